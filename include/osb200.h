@@ -1,0 +1,183 @@
+/*
+ * osb200.h -- C ABI of libosb200.so, the B200 (sm_100a) sparse-3D-convolution + open-vocabulary
+ * matching engine that replaces the MinkowskiEngine native backend and the driver-side torch ops on
+ * OpenScene's hot path.
+ *
+ * What each group replaces in the reference (paths relative to the reference root):
+ *   osb_coordset_* / osb_kernel_map_*   the coordinate manager inside MinkowskiEngine that
+ *        `ME.SparseTensor(feat, coords)` (run/evaluate.py:284, run/distill.py:316) and every
+ *        `ME.MinkowskiConvolution(..., kernel_size=k, stride=s)` (models/mink_unet.py:47-113) drive:
+ *        coordinate hash, tensor-stride sets, per-offset kernel maps.
+ *   osb_conv_*                          `MinkowskiConvolution.forward` / `MinkowskiConvolutionTranspose.forward`
+ *        (gather -> GEMM -> scatter-add per sparse-conv layer; models/mink_unet.py:116-174) and their autograd
+ *        backward (run/distill.py:333).
+ *   osb_bn_* / osb_relu_* ...           `MinkowskiBatchNorm` / `MinkowskiReLU` on the [N,C] feature matrix
+ *        (models/mink_unet.py:50,114).
+ *   osb_match_*                         `predictions[inds_reverse]`, `x/(|x|+1e-5)`, `.half() @ text_features.t()`,
+ *        `torch.max(pred,1)` (run/evaluate.py:288-323).
+ *   osb_voxelize_*                      `Voxelizer.voxelize` + `sparse_quantize`/`fnv_hash_vec`
+ *        (dataset/voxelizer.py:97-140, dataset/voxelization_utils.py:9-22,44-137).
+ *
+ * Conventions
+ *   - every pointer is a raw DEVICE pointer unless the name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
+ *     unless documented ("SYNC");
+ *   - the CALLER allocates every output and workspace (sizes via the *_workspace_bytes queries), so
+ *     memory stays in the caller's allocator; the library keeps no per-call state;
+ *   - every function returns 0 on success, non-zero on failure; osb_last_error() returns a
+ *     thread-local description; no exception crosses the ABI;
+ *   - there is no CPU fallback: on a machine without an sm_100 GPU every compute entry point fails.
+ */
+#ifndef OSB200_H
+#define OSB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OSB_VERSION 100
+
+/* ------------------------------------------------------------------ misc */
+int         osb_version(void);
+const char *osb_last_error(void);
+/* sm count, compute capability of the current device. */
+int osb_device_info(int *sm_count, int *cc_major, int *cc_minor);
+/* number of kernels this library has launched in this process (bench.py's `gpu_launches`). */
+int64_t osb_launch_count(void);
+
+/* --------------------------------------------------------- coordinate sets
+ * A coordinate is an int32 row (b, x, y, z).  Valid range: 0 <= b < 1024, |x|,|y|,|z| < 2^17 - 256.
+ * Internally rows are kept in Morton order (b major) -- the "internal order"; `perm[r]` is the
+ * caller's row of internal row r.
+ *
+ * Hash table: `cap` slots of 16 bytes {uint64 key, int32 row, int32 pad}, cap a power of two >= 2n.
+ */
+size_t osb_coordset_workspace_bytes(int64_t n);
+
+/* Build the tensor-stride-1 set from caller-order coordinates.
+ *   coords      in  int32 [n,4]
+ *   coords_int  out int32 [n,4]   coordinates in internal (Morton) order
+ *   perm        out int32 [n]     internal row -> caller row
+ *   inv_perm    out int32 [n]     caller row  -> internal row
+ *   slots       out 16B  [cap]    hash table over coords_int
+ *   status_host out int32 [2]     HOST: [0] bit0 = coordinate out of range, bit1 = duplicate coordinate
+ * SYNC: waits for `stream` to deliver status_host. */
+int osb_coordset_build(const int32_t *coords, int64_t n, int32_t *coords_int, int32_t *perm, int32_t *inv_perm,
+                       void *slots, int64_t cap, int32_t *status_host, void *ws, size_t ws_bytes, void *stream);
+
+/* Coarser set: unique(floor(c / new_ts) * new_ts) per batch index, Morton ordered.
+ *   coords_fine   in  int32 [n,4] (internal order)
+ *   new_ts        absolute tensor stride of the coarse set (any integer >= 1)
+ *   coords_coarse out int32 [<=n,4]
+ *   parent_of     out int32 [n]     fine row -> coarse row
+ *   n_coarse_host out int64 [1]     HOST
+ * SYNC. */
+int osb_coordset_stride(const int32_t *coords_fine, int64_t n, int32_t new_ts, int32_t *coords_coarse,
+                        int32_t *parent_of, int64_t *n_coarse_host, void *ws, size_t ws_bytes, void *stream);
+
+/* (Re)build a hash table over internal-order coordinates. */
+int osb_hash_build(const int32_t *coords_int, int64_t n, void *slots, int64_t cap, void *stream);
+
+/* Kernel map in output-stationary form: nbr[k*n_out + o] = input row at c_out[o] + delta_k*step, or -1.
+ * Offsets enumerate x fastest; odd kernel sizes are centred, even ones use delta in {0..ks-1}
+ * (region convention of the generalised sparse convolution).
+ *   pairs_per_k   out int32 [K] (may be NULL): number of valid pairs per offset. */
+int osb_kernel_map_build(const int32_t *coords_out, int64_t n_out, const void *slots_in, int64_t cap_in,
+                         int32_t ks_x, int32_t ks_y, int32_t ks_z, int32_t step, int32_t *nbr,
+                         int32_t *pairs_per_k, void *stream);
+
+/* Swap the roles of input and output: nbr_t[k*n_in + i] = o  iff  nbr[k*n_out + o] = i  (else -1). */
+int osb_kernel_map_transpose(const int32_t *nbr, int64_t n_out, int32_t K, int32_t *nbr_t, int64_t n_in,
+                             void *stream);
+
+/* ----------------------------------------------------------- sparse conv
+ * Generic fp32 path (CUDA cores; any channel counts).  out[o,:] = sum_k in[nbr[k][o],:] @ W[k]
+ *   in   fp32 [n_in, cin] (row stride ld_in floats)     w  fp32 [K, cin, cout]
+ *   out  fp32 [n_out, cout]
+ *   transpose_w != 0: use W[k]^T, i.e. w is [K, cout, cin] (dgrad). */
+int osb_conv_fwd_f32(const float *in, int64_t ld_in, const int32_t *nbr, int64_t n_out, int32_t K,
+                     const float *w, int32_t cin, int32_t cout, int32_t transpose_w, float *out, void *stream);
+
+/* Weight gradient: gw[k] = sum_o in[nbr[k][o],:]^T gout[o,:]   (gw fp32 [K,cin,cout], overwritten). */
+int osb_conv_wgrad_f32(const float *in, const int32_t *nbr, int64_t n_out, int32_t K, const float *gout,
+                       int32_t cin, int32_t cout, float *gw, void *stream);
+
+/* Tensor-core path (tcgen05, bf16x3 split-fp32 operands, fp32 accumulation in TMEM).
+ *
+ * Activation "split" layout: a row of C channels (C % 32 == 0) is 4*C bytes; every 32-channel block is
+ * one 128-byte line [bf16 hi x32 | bf16 lo x32] with hi = bf16_rn(v), lo = bf16_rn(v - hi).
+ * Packed weights (osb_conv_pack_weights): per offset k, cout_pad rows of the same split layout over
+ * cin, i.e. the K-major B operand.
+ *
+ *   src0/src1   split rows, c0 and c1 channels (src1 may be NULL with c1 = 0): the conv input is the
+ *               column concatenation [src0 | src1] -- `ME.cat` without materialising it
+ *   nbr         int32 [K, n_out]  (NULL with K == 1 means identity: a 1x1x1 conv)
+ *   wpack       packed weights for cin = c0 + c1
+ *   scale/shift fp32 [cout] or NULL: y = acc*scale + shift   (eval-mode BatchNorm folded)
+ *   res         residual added before ReLU: split rows [n_out, cout] or NULL
+ *   relu        != 0 applies max(y, 0)
+ *   out_split   split rows [n_out, cout] or NULL
+ *   out_f32     fp32 [n_out, cout] or NULL; out_row_map (int32 [n_out] or NULL) scatters fp32 rows:
+ *               row o is written to out_f32[out_row_map[o]]
+ */
+size_t osb_conv_packed_weight_bytes(int32_t K, int32_t cin, int32_t cout);
+int osb_conv_pack_weights(const float *w, int32_t K, int32_t cin, int32_t cout, int32_t transpose_w,
+                          void *wpack, void *stream);
+int osb_conv_fwd_tc(const void *src0, int32_t c0, int64_t n_src0, const void *src1, int32_t c1, int64_t n_src1,
+                    const int32_t *nbr, int64_t n_out, int32_t K, const void *wpack, int32_t cout,
+                    const float *scale, const float *shift, const void *res, int32_t relu, void *out_split,
+                    float *out_f32, const int32_t *out_row_map, void *stream);
+
+/* Stem: fused kernel-map probe + conv for tiny cin (<= 4), fp32 FMA.  One launch replaces the
+ * 5x5x5 map build (125 probes / voxel) and the 3->32 convolution of `conv0p1s1`.
+ *   in  fp32 [n, cin] internal order;  w fp32 [K, cin, cout];  epilogue as osb_conv_fwd_tc. */
+int osb_conv_stem_fused(const float *in, int32_t cin, const int32_t *coords, int64_t n, const void *slots,
+                        int64_t cap, int32_t ks, int32_t step, const float *w, int32_t cout, const float *scale,
+                        const float *shift, int32_t relu, void *out_split, float *out_f32, void *stream);
+
+/* fp32 [n,c] <-> split rows. */
+int osb_f32_to_split(const float *in, int64_t n, int32_t c, void *out_split, void *stream);
+int osb_split_to_f32(const void *in_split, int64_t n, int32_t c, float *out, void *stream);
+
+/* ------------------------------------------------------ row-wise helpers */
+/* out[r,:] = in[idx[r],:]  (fp32 rows of c floats; idx int32) */
+int osb_gather_rows_f32(const float *in, const int32_t *idx, int64_t n_out, int32_t c, float *out, void *stream);
+
+/* ------------------------------------------------- open-vocabulary match
+ * One pass over the voxel features per query point p (v = inds_reverse[p], or p when NULL):
+ *   a = feat[v,:] (fp32 or fp16);  if normalize: a = a / (|a| + 1e-5)
+ *   s = fp16( fp16(a) . text[k,:] )  with fp32 accumulation  (text fp16 [K, C] row major)
+ *   scores[p,k] = s (fp16, may be NULL), label[p] = argmax_k s (first maximum), smax[p] = max_k s (may be NULL)
+ * Mirrors run/evaluate.py:290-292 (distill), :294-296 (fusion), :303-310 (the two normalised products). */
+int osb_match_scores(const void *feat, int32_t feat_is_f16, int64_t n_vox, int32_t c, const int64_t *inds_reverse,
+                     int64_t n_pts, const void *text_f16, int32_t k_text, int32_t normalize, void *scores_f16,
+                     int64_t *label, float *smax, void *stream);
+/* Ensemble select + final product (run/evaluate.py:316-322):
+ *   m = smax3d[p] < smax2d[p];  fe = m ? feat2d_f16[v] : fp16(feat3d[v]);  scores = fe @ text^T;  label = argmax
+ *   feat_out_f16 (may be NULL) receives fe. */
+int osb_match_ensemble(const float *feat3d, const void *feat2d_f16, int64_t n_vox, int32_t c,
+                       const int64_t *inds_reverse, int64_t n_pts, const float *smax3d, const float *smax2d,
+                       const void *text_f16, int32_t k_text, void *scores_f16, int64_t *label, void *feat_out_f16,
+                       void *stream);
+
+/* ------------------------------------------------------------- voxeliser
+ * coords (fp32 or fp64 [n,3]) -> c = floor([p,1] . M^T[:, :3]) with M the HOST 4x4 row-major fp64 matrix,
+ * c -= min(c), FNV-64 key (multiply-then-xor over uint64 words), unique by ascending key keeping the
+ * FIRST occurrence (np.unique semantics).
+ *   coords_vox    out int32 [<=n,3]    voxel coordinates, in ascending-key order
+ *   inds          out int64 [<=n]      first-occurrence point index per voxel
+ *   inds_reverse  out int64 [n]        voxel row of every point
+ *   n_vox_host    out int64 [1] HOST;  min_host out fp64 [3] HOST (the subtracted minimum)
+ * SYNC. */
+size_t osb_voxelize_workspace_bytes(int64_t n);
+int osb_voxelize(const void *coords, int32_t coords_is_f64, int64_t n, const double *matrix_host,
+                 int32_t *coords_vox, int64_t *inds, int64_t *inds_reverse, int64_t *n_vox_host,
+                 double *min_host, void *ws, size_t ws_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OSB200_H */

@@ -1,0 +1,297 @@
+// Coordinate sets, hash tables and kernel maps (integer work, HBM/L2 bound).
+//
+// Replaces the coordinate manager inside MinkowskiEngine that the reference drives through
+// ME.SparseTensor(...) (run/evaluate.py:284) and the strided / 3x3x3 / 5x5x5 convolutions of
+// models/mink_unet.py:47-113.  Row order inside the library is Morton order so that a tile of
+// consecutive rows is a compact surface patch whose 27-neighbourhoods overlap (gather locality).
+#include "common.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <stdarg.h>
+#include <string.h>
+
+namespace osb {
+
+static thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+__device__ __forceinline__ int floordiv(int a, int s) { return a >= 0 ? a / s : -((-a + s - 1) / s); }
+
+// ------------------------------------------------------------------------------------ kernels
+__global__ void k_morton_from_coords(const int4 *__restrict__ coords, int64_t n, int32_t new_ts,
+                                     uint64_t *__restrict__ morton, int32_t *__restrict__ idx,
+                                     int32_t *__restrict__ status) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int4 c = coords[i];  // (b, x, y, z)
+  bool bad = c.x < 0 || c.x >= 1024 || abs(c.y) >= kCoordLimit || abs(c.z) >= kCoordLimit || abs(c.w) >= kCoordLimit;
+  if (bad) { atomicOr(status, 1); c = make_int4(0, 0, 0, 0); }
+  if (new_ts > 1) {
+    c.y = floordiv(c.y, new_ts) * new_ts;
+    c.z = floordiv(c.z, new_ts) * new_ts;
+    c.w = floordiv(c.w, new_ts) * new_ts;
+  }
+  morton[i] = morton_key(c.x, c.y, c.z, c.w);
+  idx[i] = (int32_t)i;
+}
+
+// level 0: permute coordinates into Morton order, build inverse permutation, flag duplicates
+__global__ void k_permute_coords(const int4 *__restrict__ coords, const int32_t *__restrict__ perm,
+                                 const uint64_t *__restrict__ morton_sorted, int64_t n,
+                                 int4 *__restrict__ coords_int, int32_t *__restrict__ inv_perm,
+                                 int32_t *__restrict__ status) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  int32_t p = perm[r];
+  coords_int[r] = coords[p];
+  inv_perm[p] = (int32_t)r;
+  if (r > 0 && morton_sorted[r] == morton_sorted[r - 1]) atomicOr(status, 2);
+}
+
+__global__ void k_hash_clear(HashSlot *__restrict__ slots, int64_t cap) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cap) return;
+  reinterpret_cast<int4 *>(slots)[i] = make_int4(-1, -1, -1, 0);
+}
+
+__global__ void k_hash_insert(const int4 *__restrict__ coords_int, int64_t n, HashSlot *__restrict__ slots,
+                              uint64_t mask) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  int4 c = coords_int[r];
+  const uint64_t key = pack_key(c.x, c.y, c.z, c.w);
+  uint64_t s = hash_u64(key) & mask;
+  while (true) {
+    unsigned long long prev = atomicCAS(&slots[s].key, (unsigned long long)kEmptyKey, (unsigned long long)key);
+    if (prev == kEmptyKey || prev == key) { slots[s].row = (int32_t)r; return; }
+    s = (s + 1) & mask;
+  }
+}
+
+// stride: heads of runs of equal parent key in the sorted order
+__global__ void k_run_heads(const uint64_t *__restrict__ key_sorted, int64_t n, int32_t *__restrict__ heads) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  heads[j] = (j == 0 || key_sorted[j] != key_sorted[j - 1]) ? 1 : 0;
+}
+
+__global__ void k_emit_coarse(const int4 *__restrict__ coords_fine, const int32_t *__restrict__ order,
+                              const int32_t *__restrict__ heads, const int32_t *__restrict__ ids, int64_t n,
+                              int32_t new_ts, int4 *__restrict__ coords_coarse, int32_t *__restrict__ parent_of) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int32_t child = order[j];
+  const int32_t id = ids[j] - 1;  // inclusive scan of heads
+  parent_of[child] = id;
+  if (heads[j]) {
+    int4 c = coords_fine[child];
+    c.y = floordiv(c.y, new_ts) * new_ts;
+    c.z = floordiv(c.z, new_ts) * new_ts;
+    c.w = floordiv(c.w, new_ts) * new_ts;
+    coords_coarse[id] = c;
+  }
+}
+
+// kernel map: grid.y = k; one thread per output row
+__global__ void k_kernel_map(const int4 *__restrict__ coords_out, int64_t n_out, const HashSlot *__restrict__ slots,
+                             uint64_t mask, int ksx, int ksy, int ksz, int step, int32_t *__restrict__ nbr,
+                             int32_t *__restrict__ pairs_per_k) {
+  const int k = blockIdx.y;
+  int ix = k % ksx, iy = (k / ksx) % ksy, iz = k / (ksx * ksy);
+  const int dx = ((ksx & 1) ? ix - ksx / 2 : ix) * step;
+  const int dy = ((ksy & 1) ? iy - ksy / 2 : iy) * step;
+  const int dz = ((ksz & 1) ? iz - ksz / 2 : iz) * step;
+  int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int hit = 0;
+  if (o < n_out) {
+    int4 c = coords_out[o];
+    const uint64_t key = pack_key(c.x, c.y + dx, c.z + dy, c.w + dz);
+    const int row = hash_lookup(slots, mask, key);
+    nbr[(int64_t)k * n_out + o] = row;
+    hit = row >= 0;
+  }
+  if (pairs_per_k != nullptr) {
+    int cnt = __syncthreads_count(hit);
+    if (threadIdx.x == 0 && cnt) atomicAdd(pairs_per_k + k, cnt);
+  }
+}
+
+__global__ void k_fill_i32(int32_t *__restrict__ p, int64_t n, int32_t v) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+__global__ void k_kernel_map_transpose(const int32_t *__restrict__ nbr, int64_t n_out, int K,
+                                       int32_t *__restrict__ nbr_t, int64_t n_in) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_out * K) return;
+  const int k = (int)(t / n_out);
+  const int64_t o = t - (int64_t)k * n_out;
+  const int32_t i = nbr[t];
+  if (i >= 0) nbr_t[(int64_t)k * n_in + i] = (int32_t)o;
+}
+
+// ------------------------------------------------------------------------------ workspace carve
+struct Carver {
+  char *p;
+  size_t left;
+  bool ok = true;
+  template <typename T>
+  T *take(size_t count) {
+    size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+    if (bytes > left) { ok = false; return nullptr; }
+    T *r = reinterpret_cast<T *>(p);
+    p += bytes;
+    left -= bytes;
+    return r;
+  }
+};
+
+static size_t cub_sort_bytes(int64_t n) {
+  size_t b = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, b, (const uint64_t *)nullptr, (uint64_t *)nullptr, (const int32_t *)nullptr,
+                                  (int32_t *)nullptr, (int)n, 0, 64, (cudaStream_t)0);
+  return b;
+}
+static size_t cub_scan_bytes(int64_t n) {
+  size_t b = 0;
+  cub::DeviceScan::InclusiveSum(nullptr, b, (const int32_t *)nullptr, (int32_t *)nullptr, (int)n, (cudaStream_t)0);
+  return b;
+}
+
+}  // namespace osb
+
+using namespace osb;
+
+extern "C" {
+
+int osb_version(void) { return OSB_VERSION; }
+const char *osb_last_error(void) { return osb::g_err; }
+int64_t osb_launch_count(void) { return osb::g_launches.load(); }
+
+int osb_device_info(int *sm_count, int *cc_major, int *cc_minor) {
+  int dev = 0;
+  OSB_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  OSB_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  return 0;
+}
+
+size_t osb_coordset_workspace_bytes(int64_t n) {
+  if (n < 1) n = 1;
+  size_t per = (size_t)n * (8 + 8 + 4 + 4 + 4 + 4) + 8 * 256;
+  return per + cub_sort_bytes(n) + cub_scan_bytes(n) + 1024;
+}
+
+int osb_hash_build(const int32_t *coords_int, int64_t n, void *slots, int64_t cap, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  OSB_CHECK(cap >= 2 && (cap & (cap - 1)) == 0 && cap >= 2 * n, "osb_hash_build: cap=%lld must be a power of two >= 2n (n=%lld)",
+            (long long)cap, (long long)n);
+  k_hash_clear<<<(unsigned)ceil_div(cap, 256), 256, 0, stream>>>((HashSlot *)slots, cap);
+  OSB_LAUNCH_CHECK();
+  if (n > 0) {
+    k_hash_insert<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>((const int4 *)coords_int, n, (HashSlot *)slots,
+                                                                  (uint64_t)cap - 1);
+    OSB_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+int osb_coordset_build(const int32_t *coords, int64_t n, int32_t *coords_int, int32_t *perm, int32_t *inv_perm,
+                       void *slots, int64_t cap, int32_t *status_host, void *ws, size_t ws_bytes, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  OSB_CHECK(n > 0 && n < (1ll << 31) - 1024, "osb_coordset_build: n=%lld out of range", (long long)n);
+  Carver cv{(char *)ws, ws_bytes};
+  uint64_t *morton = cv.take<uint64_t>(n);
+  uint64_t *morton_s = cv.take<uint64_t>(n);
+  int32_t *idx = cv.take<int32_t>(n);
+  int32_t *status = cv.take<int32_t>(64);
+  size_t sort_bytes = cub_sort_bytes(n);
+  void *cub_tmp = cv.take<char>(sort_bytes);
+  OSB_CHECK(cv.ok, "osb_coordset_build: workspace too small (%zu bytes)", ws_bytes);
+  OSB_CUDA(cudaMemsetAsync(status, 0, 8, stream));
+  const unsigned nb = (unsigned)ceil_div(n, 256);
+  k_morton_from_coords<<<nb, 256, 0, stream>>>((const int4 *)coords, n, 1, morton, idx, status);
+  OSB_LAUNCH_CHECK();
+  OSB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, sort_bytes, morton, morton_s, idx, perm, (int)n, 0, 64, stream));
+  count_launch(4);
+  k_permute_coords<<<nb, 256, 0, stream>>>((const int4 *)coords, perm, morton_s, n, (int4 *)coords_int, inv_perm, status);
+  OSB_LAUNCH_CHECK();
+  if (osb_hash_build(coords_int, n, slots, cap, stream_)) return 1;
+  OSB_CUDA(cudaMemcpyAsync(status_host, status, 8, cudaMemcpyDeviceToHost, stream));
+  OSB_CUDA(cudaStreamSynchronize(stream));
+  return 0;
+}
+
+int osb_coordset_stride(const int32_t *coords_fine, int64_t n, int32_t new_ts, int32_t *coords_coarse,
+                        int32_t *parent_of, int64_t *n_coarse_host, void *ws, size_t ws_bytes, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  OSB_CHECK(n > 0 && new_ts >= 1, "osb_coordset_stride: bad arguments n=%lld new_ts=%d", (long long)n, new_ts);
+  Carver cv{(char *)ws, ws_bytes};
+  uint64_t *key = cv.take<uint64_t>(n);
+  uint64_t *key_s = cv.take<uint64_t>(n);
+  int32_t *idx = cv.take<int32_t>(n);
+  int32_t *order = cv.take<int32_t>(n);
+  int32_t *heads = cv.take<int32_t>(n);
+  int32_t *ids = cv.take<int32_t>(n);
+  int32_t *status = cv.take<int32_t>(64);
+  size_t sort_bytes = cub_sort_bytes(n), scan_bytes = cub_scan_bytes(n);
+  void *cub_tmp = cv.take<char>(sort_bytes > scan_bytes ? sort_bytes : scan_bytes);
+  OSB_CHECK(cv.ok, "osb_coordset_stride: workspace too small (%zu bytes)", ws_bytes);
+  OSB_CUDA(cudaMemsetAsync(status, 0, 8, stream));
+  const unsigned nb = (unsigned)ceil_div(n, 256);
+  k_morton_from_coords<<<nb, 256, 0, stream>>>((const int4 *)coords_fine, n, new_ts, key, idx, status);
+  OSB_LAUNCH_CHECK();
+  OSB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, sort_bytes, key, key_s, idx, order, (int)n, 0, 64, stream));
+  count_launch(4);
+  k_run_heads<<<nb, 256, 0, stream>>>(key_s, n, heads);
+  OSB_LAUNCH_CHECK();
+  OSB_CUDA(cub::DeviceScan::InclusiveSum(cub_tmp, scan_bytes, heads, ids, (int)n, stream));
+  count_launch(2);
+  k_emit_coarse<<<nb, 256, 0, stream>>>((const int4 *)coords_fine, order, heads, ids, n, new_ts, (int4 *)coords_coarse,
+                                        parent_of);
+  OSB_LAUNCH_CHECK();
+  int32_t last = 0;
+  OSB_CUDA(cudaMemcpyAsync(&last, ids + (n - 1), 4, cudaMemcpyDeviceToHost, stream));
+  OSB_CUDA(cudaStreamSynchronize(stream));
+  *n_coarse_host = last;
+  return 0;
+}
+
+int osb_kernel_map_build(const int32_t *coords_out, int64_t n_out, const void *slots_in, int64_t cap_in, int32_t ks_x,
+                         int32_t ks_y, int32_t ks_z, int32_t step, int32_t *nbr, int32_t *pairs_per_k, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int K = ks_x * ks_y * ks_z;
+  OSB_CHECK(n_out > 0 && K >= 1 && K <= 1024 && step >= 1, "osb_kernel_map_build: bad arguments");
+  OSB_CHECK((cap_in & (cap_in - 1)) == 0, "osb_kernel_map_build: cap must be a power of two");
+  if (pairs_per_k) OSB_CUDA(cudaMemsetAsync(pairs_per_k, 0, sizeof(int32_t) * K, stream));
+  dim3 grid((unsigned)ceil_div(n_out, 256), K);
+  k_kernel_map<<<grid, 256, 0, stream>>>((const int4 *)coords_out, n_out, (const HashSlot *)slots_in,
+                                         (uint64_t)cap_in - 1, ks_x, ks_y, ks_z, step, nbr, pairs_per_k);
+  OSB_LAUNCH_CHECK();
+  return 0;
+}
+
+int osb_kernel_map_transpose(const int32_t *nbr, int64_t n_out, int32_t K, int32_t *nbr_t, int64_t n_in, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  OSB_CHECK(n_out > 0 && n_in > 0 && K >= 1, "osb_kernel_map_transpose: bad arguments");
+  k_fill_i32<<<(unsigned)ceil_div(n_in * K, 256), 256, 0, stream>>>(nbr_t, n_in * K, -1);
+  OSB_LAUNCH_CHECK();
+  k_kernel_map_transpose<<<(unsigned)ceil_div(n_out * K, 256), 256, 0, stream>>>(nbr, n_out, K, nbr_t, n_in);
+  OSB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

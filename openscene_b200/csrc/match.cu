@@ -1,0 +1,186 @@
+// Open-vocabulary matching: voxel->point gather, optional L2 normalisation, fp16 product with the
+// CLIP text embeddings, row max / argmax -- one pass over the features, nothing materialised at
+// [N_pts, C].  Replaces the torch ops at run/evaluate.py:288-323.
+//
+// HBM-bound: 4*C bytes read per point (3 KB at C = 768) against 2*C*K flops; one warp owns one
+// point, the text matrix (K*C*2 bytes, <= 245 KB) stays in L1/L2.
+#include "common.cuh"
+#include <algorithm>
+
+namespace osb {
+
+template <int NP>  // half2 pairs per lane: C = 64 * NP
+struct RowRegs {
+  float v[2 * NP];
+};
+
+// load a feature row into registers as the fp16-rounded values the reference multiplies
+template <int NP, bool F16, bool NORMALIZE>
+__device__ __forceinline__ void load_row(const void *__restrict__ feat, int64_t row, int lane, RowRegs<NP> &r) {
+  constexpr int C = 64 * NP;
+  float ss = 0.f;
+  if (F16) {
+    const __half2 *p = reinterpret_cast<const __half2 *>(feat) + row * (C / 2);
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      const float2 f = __half22float2(__ldg(p + lane + 32 * j));
+      r.v[2 * j] = f.x; r.v[2 * j + 1] = f.y;
+      ss += f.x * f.x + f.y * f.y;
+    }
+  } else {
+    const float2 *p = reinterpret_cast<const float2 *>(feat) + row * (C / 2);
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      const float2 f = __ldg(p + lane + 32 * j);
+      r.v[2 * j] = f.x; r.v[2 * j + 1] = f.y;
+      ss += f.x * f.x + f.y * f.y;
+    }
+  }
+  if (NORMALIZE) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    float nrm = sqrtf(ss);
+    if (F16) {
+      // the reference takes norm / +1e-5 / division on an fp16 tensor (evaluate.py:303-305)
+      nrm = __half2float(__float2half_rn(nrm));
+      const float d = __half2float(__float2half_rn(nrm + 1e-5f));
+#pragma unroll
+      for (int j = 0; j < 2 * NP; ++j) r.v[j] = __half2float(__float2half_rn(r.v[j] / d));
+    } else {
+      const float d = nrm + 1e-5f;
+#pragma unroll
+      for (int j = 0; j < 2 * NP; ++j) r.v[j] = __half2float(__float2half_rn(r.v[j] / d));
+    }
+  } else if (!F16) {
+#pragma unroll
+    for (int j = 0; j < 2 * NP; ++j) r.v[j] = __half2float(__float2half_rn(r.v[j]));   // .half()
+  }
+}
+
+template <int NP>
+__device__ __forceinline__ void score_row(const RowRegs<NP> &r, const __half2 *__restrict__ text, int k_text, int lane,
+                                          __half *__restrict__ scores_row, float &best, int &best_k) {
+  constexpr int C = 64 * NP;
+  best = -INFINITY;
+  best_k = 0;
+  for (int k = 0; k < k_text; ++k) {
+    const __half2 *t = text + (int64_t)k * (C / 2);
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      const float2 f = __half22float2(__ldg(t + lane + 32 * j));
+      acc = fmaf(r.v[2 * j], f.x, acc);
+      acc = fmaf(r.v[2 * j + 1], f.y, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    const __half h = __float2half_rn(acc);
+    const float s = __half2float(h);
+    if (scores_row != nullptr && lane == 0) scores_row[k] = h;
+    if (s > best) { best = s; best_k = k; }
+  }
+}
+
+template <int NP, bool F16, bool NORMALIZE>
+__global__ void __launch_bounds__(256)
+k_match_scores(const void *__restrict__ feat, const int64_t *__restrict__ inds_reverse, int64_t n_pts,
+               const __half2 *__restrict__ text, int k_text, __half *__restrict__ scores, int64_t *__restrict__ label,
+               float *__restrict__ smax) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t p = warp; p < n_pts; p += nwarps) {
+    const int64_t v = inds_reverse ? inds_reverse[p] : p;
+    RowRegs<NP> r;
+    load_row<NP, F16, NORMALIZE>(feat, v, lane, r);
+    float best; int best_k;
+    score_row<NP>(r, text, k_text, lane, scores ? scores + p * k_text : nullptr, best, best_k);
+    if (lane == 0) {
+      if (label) label[p] = best_k;
+      if (smax) smax[p] = best;
+    }
+  }
+}
+
+template <int NP>
+__global__ void __launch_bounds__(256)
+k_match_ensemble(const float *__restrict__ feat3d, const __half *__restrict__ feat2d, const int64_t *__restrict__ inds_reverse,
+                 int64_t n_pts, const float *__restrict__ smax3d, const float *__restrict__ smax2d,
+                 const __half2 *__restrict__ text, int k_text, __half *__restrict__ scores, int64_t *__restrict__ label,
+                 __half *__restrict__ feat_out) {
+  constexpr int C = 64 * NP;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t p = warp; p < n_pts; p += nwarps) {
+    const int64_t v = inds_reverse ? inds_reverse[p] : p;
+    const bool use2d = smax3d[p] < smax2d[p];
+    RowRegs<NP> r;
+    if (use2d) load_row<NP, true, false>(feat2d, v, lane, r);
+    else       load_row<NP, false, false>(feat3d, v, lane, r);
+    if (feat_out) {
+      __half2 *o = reinterpret_cast<__half2 *>(feat_out) + p * (C / 2);
+#pragma unroll
+      for (int j = 0; j < NP; ++j) o[lane + 32 * j] = __floats2half2_rn(r.v[2 * j], r.v[2 * j + 1]);
+    }
+    float best; int best_k;
+    score_row<NP>(r, text, k_text, lane, scores ? scores + p * k_text : nullptr, best, best_k);
+    if (lane == 0 && label) label[p] = best_k;
+  }
+}
+
+static unsigned match_grid(int64_t n_pts) {
+  return (unsigned)std::min<int64_t>(ceil_div(n_pts, 8), 148 * 8);
+}
+
+}  // namespace osb
+
+using namespace osb;
+
+extern "C" {
+
+int osb_match_scores(const void *feat, int32_t feat_is_f16, int64_t n_vox, int32_t c, const int64_t *inds_reverse,
+                     int64_t n_pts, const void *text_f16, int32_t k_text, int32_t normalize, void *scores_f16,
+                     int64_t *label, float *smax, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  OSB_CHECK(c == 512 || c == 768, "osb_match_scores: feature width %d unsupported (OpenScene uses 512 / 768)", c);
+  OSB_CHECK(k_text >= 1 && n_vox > 0, "osb_match_scores: bad shape");
+  if (n_pts == 0) return 0;
+  const unsigned grid = match_grid(n_pts);
+  const __half2 *text = (const __half2 *)text_f16;
+  __half *scores = (__half *)scores_f16;
+#define OSB_MS(NP, F16, NRM) \
+  k_match_scores<NP, F16, NRM><<<grid, 256, 0, stream>>>(feat, inds_reverse, n_pts, text, k_text, scores, label, smax)
+  if (c == 768) {
+    if (feat_is_f16) { if (normalize) OSB_MS(12, true, true); else OSB_MS(12, true, false); }
+    else             { if (normalize) OSB_MS(12, false, true); else OSB_MS(12, false, false); }
+  } else {
+    if (feat_is_f16) { if (normalize) OSB_MS(8, true, true); else OSB_MS(8, true, false); }
+    else             { if (normalize) OSB_MS(8, false, true); else OSB_MS(8, false, false); }
+  }
+#undef OSB_MS
+  OSB_LAUNCH_CHECK();
+  return 0;
+}
+
+int osb_match_ensemble(const float *feat3d, const void *feat2d_f16, int64_t n_vox, int32_t c, const int64_t *inds_reverse,
+                       int64_t n_pts, const float *smax3d, const float *smax2d, const void *text_f16, int32_t k_text,
+                       void *scores_f16, int64_t *label, void *feat_out_f16, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  OSB_CHECK(c == 512 || c == 768, "osb_match_ensemble: feature width %d unsupported", c);
+  OSB_CHECK(k_text >= 1 && n_vox > 0, "osb_match_ensemble: bad shape");
+  if (n_pts == 0) return 0;
+  const unsigned grid = match_grid(n_pts);
+  if (c == 768)
+    k_match_ensemble<12><<<grid, 256, 0, stream>>>(feat3d, (const __half *)feat2d_f16, inds_reverse, n_pts, smax3d, smax2d,
+                                                   (const __half2 *)text_f16, k_text, (__half *)scores_f16, label,
+                                                   (__half *)feat_out_f16);
+  else
+    k_match_ensemble<8><<<grid, 256, 0, stream>>>(feat3d, (const __half *)feat2d_f16, inds_reverse, n_pts, smax3d, smax2d,
+                                                  (const __half2 *)text_f16, k_text, (__half *)scores_f16, label,
+                                                  (__half *)feat_out_f16);
+  OSB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

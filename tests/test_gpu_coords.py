@@ -1,0 +1,108 @@
+"""Coordinate sets and kernel maps from libosb200 against the oracle -- exact (integer / index work).
+Canonical form: the SET of (k, in_coord, out_coord) triples (row order inside a level is free)."""
+import numpy as np
+import pytest
+import torch
+
+from openscene_b200 import synth
+from tests.util import kmap_triples
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device('cuda:0')
+
+
+def _triples_gpu(km, cin, cout):
+    nbr = km.nbr.cpu().numpy()
+    cin, cout = cin.cpu().numpy(), cout.cpu().numpy()
+    s = set()
+    for k in range(km.K):
+        o = np.nonzero(nbr[k] >= 0)[0]
+        for oo, ii in zip(o, nbr[k][o]):
+            s.add((k, tuple(cin[ii]), tuple(cout[oo])))
+    return s
+
+
+def _triples_oracle(maps, cin, cout):
+    s = set()
+    for k, (ii, oo) in enumerate(maps):
+        for i, o in zip(ii.tolist(), oo.tolist()):
+            s.add((k, tuple(cin[i]), tuple(cout[o])))
+    return s
+
+
+@pytest.mark.parametrize('case', ['cloud', 'negative', 'room', 'batch2'])
+def test_sets_and_maps_match_oracle(case):
+    from openscene_b200.coords import CoordinateManager
+    from oracle import me_cpu
+    if case == 'cloud':
+        c = synth.random_cloud(3000, 40, seed=0)
+    elif case == 'negative':
+        c = synth.random_cloud(2000, 30, seed=1)
+        c[:, 1:] -= 17
+    elif case == 'room':
+        c = synth.scene('tiny')
+    else:
+        c = synth.random_cloud(1500, 24, seed=2, batch=2)
+    cm = CoordinateManager(torch.from_numpy(c).to(_dev()))
+    om = me_cpu.CoordinateManager(c)
+    # level 0 keeps every row, perm is a permutation
+    perm = cm.perm.cpu().numpy()
+    assert sorted(perm.tolist()) == list(range(len(c)))
+    assert np.array_equal(cm.sets[1].coords.cpu().numpy(), c[perm])
+    assert np.array_equal(cm.coords_external(1).cpu().numpy(), c)
+    ts = 1
+    for _ in range(4):
+        new = cm.stride(ts, 2)
+        om.stride(ts, 2)
+        got = cm.sets[new].coords.cpu().numpy()
+        assert {tuple(r) for r in got.tolist()} == {tuple(r) for r in om.coords[new].tolist()}
+        assert len(got) == len(om.coords[new])
+        # parent_of is consistent with floor division
+        par = cm.parent_of[(ts, new)].cpu().numpy()
+        fine = cm.sets[ts].coords.cpu().numpy().astype(np.int64)
+        exp = fine.copy()
+        exp[:, 1:] = np.floor_divide(fine[:, 1:], new) * new
+        assert np.array_equal(got[par], exp)
+        # 2x2x2 stride-2 map and 3x3x3 map at this level
+        for (ti, to, ks) in [(ts, new, 2), (ts, ts, 3)]:
+            km = cm.kernel_map(ti, to, ks)
+            t_gpu = _triples_gpu(km, cm.sets[ti].coords, cm.sets[to].coords)
+            t_ref = _triples_oracle(om.kernel_map(ti, to, ks), om.coords[ti], om.coords[to])
+            assert t_gpu == t_ref
+            assert km.num_pairs() == len(t_ref)
+        ts = new
+    km5 = cm.kernel_map(1, 1, 5)
+    assert _triples_gpu(km5, cm.sets[1].coords, cm.sets[1].coords) == \
+        _triples_oracle(om.kernel_map(1, 1, 5), om.coords[1], om.coords[1])
+    # transposed map is the exact swap
+    km = cm.kernel_map(1, 2, 2)
+    nt = km.transposed().nbr.cpu().numpy()
+    n = km.nbr.cpu().numpy()
+    for k in range(8):
+        o = np.nonzero(n[k] >= 0)[0]
+        assert np.array_equal(nt[k][n[k][o]], o)
+        assert (nt[k] >= 0).sum() == len(o)
+    assert (nt >= 0).sum() == len(c)          # every fine voxel has exactly one parent
+
+
+def test_duplicates_and_range_fail_loudly():
+    from openscene_b200.coords import CoordinateManager
+    c = torch.tensor([[0, 1, 2, 3], [0, 1, 2, 3]], dtype=torch.int32, device=_dev())
+    with pytest.raises(RuntimeError, match='duplicate'):
+        CoordinateManager(c)
+    c = torch.tensor([[0, 1 << 18, 2, 3]], dtype=torch.int32, device=_dev())
+    with pytest.raises(RuntimeError, match='out of range'):
+        CoordinateManager(c)
+
+
+def test_morton_order_is_spatially_compact():
+    from openscene_b200.coords import CoordinateManager
+    c = synth.scene('tiny')
+    cm = CoordinateManager(torch.from_numpy(c).to(_dev()))
+    ci = cm.sets[1].coords.cpu().numpy()[:, 1:].astype(np.float64)
+    d_sorted = np.linalg.norm(np.diff(ci, axis=0), axis=1).mean()
+    d_input = np.linalg.norm(np.diff(c[:, 1:].astype(np.float64), axis=0), axis=1).mean()
+    assert d_sorted < 0.25 * d_input
