@@ -1,0 +1,422 @@
+// Sparse convolution on 5th-gen tensor cores: TMA gather4 -> shared memory -> tcgen05.mma -> TMEM.
+//
+//   out[o,:] = epilogue( sum_k  in[nbr[k][o], :] @ W[k] )         (output-stationary, no atomics)
+//
+// Replaces MinkowskiConvolution / MinkowskiConvolutionTranspose forward (models/mink_unet.py:116-174)
+// for channel counts that are multiples of 32, with BatchNorm(eval) / residual / ReLU / `ME.cat`
+// folded in (mink_unet.py:50,114,147; BasicBlock).
+//
+// Numerics: fp32 operands are carried as split bf16 pairs (v = hi + lo) and every product is
+// evaluated as hi*Whi + hi*Wlo + lo*Whi on kind::f16 (bf16) MMAs with fp32 accumulation in TMEM:
+// ~2^-16 relative operand error, i.e. fp32-grade results at 1.5x the tensor time of one TF32 pass.
+//
+// One CTA = 128 output rows x NT output channels.  A pipeline stage holds one (offset k, 32-channel
+// block) pair: A = 128 gathered rows x 128 B (TMA tile::gather4, 128B swizzle, missing neighbours are
+// out-of-bounds rows -> hardware zero fill, no L2 traffic), B = NT weight rows x 128 B.
+// Warp roles: 0 = TMA producer (every lane issues one gather4), 1 = TMEM alloc + MMA issuer,
+// 2..5 = epilogue (TMEM -> registers -> affine/residual/ReLU -> split-bf16 or fp32 rows).
+#include "common.cuh"
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <algorithm>
+
+namespace osb {
+
+constexpr int TC_M = 128;          // rows per CTA (UMMA M)
+constexpr int TC_MAXK = 32;        // kernel offsets handled by this kernel (27, 8, 1)
+constexpr int TC_THREADS = 192;
+constexpr int TC_A_BYTES = TC_M * 128;
+
+struct ConvTcParams {
+  const int32_t *nbr;
+  int64_t n_out;
+  int K, nb0, nb1;
+  int n_src0, n_src1;
+  int cout, cout_pad, nt, stages, tmem_cols;
+  const float *scale, *shift;
+  const uint8_t *res;
+  int relu;
+  uint8_t *out_split;
+  float *out_f32;
+  const int32_t *out_row_map;
+  int use_gather4;
+};
+
+// ------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t it = 0; !done; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (it > (1u << 26)) __trap();   // a lost TMA / MMA completion must not hang the GPU
+  }
+}
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int col, int r0, int r1,
+                                            int r2, int r3) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+// K-major, 128-byte swizzle: 8-row groups 1024 B apart, descriptor version 1 (sm_100)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// ------------------------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(TC_THREADS)
+k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+          const __grid_constant__ CUtensorMap tmB, const ConvTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stage_bytes = TC_A_BYTES + p.nt * 128;
+  uint8_t *aux = smem + p.stages * stage_bytes;
+  int32_t *s_nbr = reinterpret_cast<int32_t *>(aux);                        // [K][128]
+  float *s_scale = reinterpret_cast<float *>(aux + p.K * TC_M * 4);         // [nt]
+  float *s_shift = s_scale + 256;                                           // [nt]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(s_shift + 256);             // full[8], empty[8], accum
+  uint32_t *s_misc = reinterpret_cast<uint32_t *>(bars + 17);               // [0] tmem base, [1] kmask
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t row0 = (int64_t)blockIdx.x * TC_M;
+  const int n0 = blockIdx.y * p.nt;
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + 8), accum_bar = smem_u32(bars + 16);
+
+  if (tid == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(accum_bar, 1);
+    s_misc[1] = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // TMEM allocation (whole warp), result written to smem
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_misc[0])),
+                 "r"((uint32_t)p.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  __syncthreads();   // s_misc[1] = 0 visible before the atomics below
+
+  // ---- prologue: neighbour rows of this tile -> smem, bit mask of offsets that touch the tile
+  for (int e = tid; e < p.K * TC_M; e += TC_THREADS) {
+    const int k = e >> 7, m = e & 127;
+    const int64_t o = row0 + m;
+    int32_t idx = -1;
+    if (o < p.n_out) idx = p.nbr ? __ldg(p.nbr + (int64_t)k * p.n_out + o) : (int32_t)o;
+    s_nbr[e] = idx;
+    const bool any = __any_sync(0xffffffffu, idx >= 0);
+    if (any && lane == 0) atomicOr(&s_misc[1], 1u << k);
+  }
+  for (int n = tid; n < p.nt; n += TC_THREADS) {
+    const int c = n0 + n;
+    s_scale[n] = (p.scale && c < p.cout) ? __ldg(p.scale + c) : 1.f;
+    s_shift[n] = (p.shift && c < p.cout) ? __ldg(p.shift + c) : 0.f;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = s_misc[0];
+  const uint32_t kmask = s_misc[1];
+  const int nb = p.nb0 + p.nb1;
+
+  if (warp == 0) {
+    // ================================ TMA producer =================================
+    int s = 0;
+    uint32_t phase = 0;
+    for (uint32_t km = kmask; km; km &= km - 1) {
+      const int k = __ffs(km) - 1;
+      const int4 rows = *reinterpret_cast<const int4 *>(s_nbr + k * TC_M + 4 * lane);
+      for (int cb = 0; cb < nb; ++cb) {
+        mbar_wait(empty0 + 8 * s, phase ^ 1);
+        const uint32_t a_dst = smem_u32(smem + s * stage_bytes);
+        const uint32_t fb = full0 + 8 * s;
+        if (lane == 0) {
+          mbar_expect_tx(fb, (uint32_t)stage_bytes);
+          tma_load_2d(a_dst + TC_A_BYTES, &tmB, fb, cb * 64, k * p.cout_pad + n0);
+        }
+        __syncwarp();
+        const bool first = cb < p.nb0;
+        const CUtensorMap *tm = first ? &tmA0 : &tmA1;
+        const int col = (first ? cb : cb - p.nb0) * 64;
+        const int oob = first ? p.n_src0 : p.n_src1;           // one past the last row: zero fill
+        const int r0 = rows.x >= 0 ? rows.x : oob, r1 = rows.y >= 0 ? rows.y : oob;
+        const int r2 = rows.z >= 0 ? rows.z : oob, r3 = rows.w >= 0 ? rows.w : oob;
+        if (p.use_gather4) {
+          tma_gather4(a_dst + lane * 512, tm, fb, col, r0, r1, r2, r3);
+        } else {   // same tensor map, one row per copy (debug / cross-check path)
+          tma_load_2d(a_dst + lane * 512, tm, fb, col, r0);
+          tma_load_2d(a_dst + lane * 512 + 128, tm, fb, col, r1);
+          tma_load_2d(a_dst + lane * 512 + 256, tm, fb, col, r2);
+          tma_load_2d(a_dst + lane * 512 + 384, tm, fb, col, r3);
+        }
+        if (++s == p.stages) { s = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ===================================
+    // instruction descriptor: D=f32, A=B=bf16, K-major both, N = nt, M = 128
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.nt >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+    int s = 0;
+    uint32_t phase = 0, acc = 0;
+    for (uint32_t km = kmask; km; km &= km - 1) {
+      for (int cb = 0; cb < nb; ++cb) {
+        mbar_wait(full0 + 8 * s, phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+          const uint64_t da = umma_desc(a_addr), db = umma_desc(a_addr + TC_A_BYTES);
+          // 128-byte line = [hi ch0-15 | hi ch16-31 | lo ch0-15 | lo ch16-31]; +2 per 32-byte K slice
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            umma_bf16(tmem_base, da + 2 * h, db + 2 * h, idesc, acc);       // hi * Whi
+            acc = 1;
+            umma_bf16(tmem_base, da + 2 * h, db + 2 * h + 4, idesc, 1);     // hi * Wlo
+            umma_bf16(tmem_base, da + 2 * h + 4, db + 2 * h, idesc, 1);     // lo * Whi
+          }
+          umma_commit(empty0 + 8 * s);      // frees the stage when these MMAs retire
+        }
+        __syncwarp();
+        if (++s == p.stages) { s = 0; phase ^= 1; }
+      }
+    }
+    if (lane == 0) umma_commit(accum_bar);
+    __syncwarp();
+  } else {
+    // ================================ epilogue ======================================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int m = q * 32 + lane;
+    const int64_t o = row0 + m;
+    if (kmask) {
+      mbar_wait(accum_bar, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    const bool live = o < p.n_out;
+    const int64_t orow = (live && p.out_row_map) ? (int64_t)__ldg(p.out_row_map + o) : o;
+    for (int cbo = 0; cbo < p.nt / 32; ++cbo) {
+      float y[32];
+      if (kmask) {
+        uint32_t v0[16], v1[16];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cbo * 32;
+        tmem_ld16(taddr, v0);
+        tmem_ld16(taddr + 16, v1);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { y[j] = __uint_as_float(v0[j]); y[16 + j] = __uint_as_float(v1[j]); }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) y[j] = 0.f;
+      }
+      const int c0 = n0 + cbo * 32;              // first output channel of this 32-block
+      if (!live || c0 >= p.cout) continue;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) y[j] = fmaf(y[j], s_scale[cbo * 32 + j], s_shift[cbo * 32 + j]);
+      if (p.res) {
+        const uint4 *rp = reinterpret_cast<const uint4 *>(p.res + o * (int64_t)p.cout * 4 + (c0 >> 5) * 128);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint4 hq = __ldg(rp + g), lq = __ldg(rp + 4 + g);
+          const __nv_bfloat16 *hh = reinterpret_cast<const __nv_bfloat16 *>(&hq);
+          const __nv_bfloat16 *ll = reinterpret_cast<const __nv_bfloat16 *>(&lq);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) y[g * 8 + j] += join_bf16(hh[j], ll[j]);
+        }
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
+      }
+      if (p.out_split) {
+        uint4 *op = reinterpret_cast<uint4 *>(p.out_split + o * (int64_t)p.cout * 4 + (c0 >> 5) * 128);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          __align__(16) __nv_bfloat16 hh[8], ll[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) split_bf16(y[g * 8 + j], hh[j], ll[j]);
+          op[g] = *reinterpret_cast<const uint4 *>(hh);
+          op[4 + g] = *reinterpret_cast<const uint4 *>(ll);
+        }
+      }
+      if (p.out_f32) {
+        float4 *op = reinterpret_cast<float4 *>(p.out_f32 + orow * (int64_t)p.cout + c0);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) op[g] = make_float4(y[4 * g], y[4 * g + 1], y[4 * g + 2], y[4 * g + 3]);
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols));
+  }
+}
+
+// --------------------------------------------------------------------------- weight packing
+__global__ void k_pack_weights(const float *__restrict__ w, int K, int cin, int cout, int cout_pad, int transpose_w,
+                               uint8_t *__restrict__ wpack) {
+  const int64_t total = (int64_t)K * cout_pad * cin;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % cin);
+    const int64_t kn = e / cin;
+    const int n = (int)(kn % cout_pad), k = (int)(kn / cout_pad);
+    float v = 0.f;
+    if (n < cout) v = transpose_w ? w[((int64_t)k * cout + n) * cin + c] : w[((int64_t)k * cin + c) * cout + n];
+    __nv_bfloat16 hi, lo;
+    split_bf16(v, hi, lo);
+    uint8_t *row = wpack + kn * (int64_t)cin * 4 + split_off_hi(c);
+    *reinterpret_cast<__nv_bfloat16 *>(row) = hi;
+    *reinterpret_cast<__nv_bfloat16 *>(row + 64) = lo;
+  }
+}
+
+// --------------------------------------------------------------------------- host side
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor [rows, cols_elems] with row pitch cols_elems*2 bytes; box {64 elems, box_rows}; 128B swizzle
+static int make_tmap(CUtensorMap *tm, const void *base, uint64_t cols_elems, uint64_t rows, uint32_t box_rows) {
+  auto enc = get_encode();
+  OSB_CHECK(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t gdim[2] = {cols_elems, rows};
+  cuuint64_t gstride[1] = {cols_elems * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  OSB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) base=%p cols=%llu rows=%llu box_rows=%u", (int)r, base,
+            (unsigned long long)cols_elems, (unsigned long long)rows, box_rows);
+  return 0;
+}
+
+static int g_tc_use_gather4 = 1;
+static int g_tc_smem_budget = 112 * 1024;   // per CTA -> two CTAs per SM
+
+}  // namespace osb
+
+using namespace osb;
+
+extern "C" {
+
+// test / tuning hooks (not part of the public header): 0/1 gather4, shared-memory budget per CTA
+void osb_debug_set_tc(int use_gather4, int smem_budget) {
+  if (use_gather4 >= 0) g_tc_use_gather4 = use_gather4;
+  if (smem_budget > 0) g_tc_smem_budget = smem_budget;
+}
+
+static inline int cout_pad_of(int cout) { return cout <= 256 ? (cout + 15) / 16 * 16 : (cout + 255) / 256 * 256; }
+
+size_t osb_conv_packed_weight_bytes(int32_t K, int32_t cin, int32_t cout) {
+  return (size_t)K * cout_pad_of(cout) * cin * 4;
+}
+
+int osb_conv_pack_weights(const float *w, int32_t K, int32_t cin, int32_t cout, int32_t transpose_w, void *wpack,
+                          void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  OSB_CHECK(K >= 1 && cin % 32 == 0 && cin > 0 && cout > 0, "osb_conv_pack_weights: cin (%d) must be a multiple of 32", cin);
+  const int cp = cout_pad_of(cout);
+  const int64_t total = (int64_t)K * cp * cin;
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(total, 256), 148 * 32);
+  k_pack_weights<<<grid, 256, 0, stream>>>(w, K, cin, cout, cp, transpose_w, (uint8_t *)wpack);
+  OSB_LAUNCH_CHECK();
+  return 0;
+}
+
+int osb_conv_fwd_tc(const void *src0, int32_t c0, int64_t n_src0, const void *src1, int32_t c1, int64_t n_src1,
+                    const int32_t *nbr, int64_t n_out, int32_t K, const void *wpack, int32_t cout, const float *scale,
+                    const float *shift, const void *res, int32_t relu, void *out_split, float *out_f32,
+                    const int32_t *out_row_map, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  OSB_CHECK(src0 && c0 > 0 && c0 % 32 == 0 && c1 >= 0 && c1 % 32 == 0, "osb_conv_fwd_tc: channel counts must be multiples of 32 (c0=%d c1=%d)", c0, c1);
+  OSB_CHECK((c1 == 0) == (src1 == nullptr), "osb_conv_fwd_tc: src1 / c1 mismatch");
+  OSB_CHECK(K >= 1 && K <= TC_MAXK, "osb_conv_fwd_tc: K=%d not supported (<= %d)", K, TC_MAXK);
+  OSB_CHECK(nbr != nullptr || K == 1, "osb_conv_fwd_tc: identity map needs K == 1");
+  OSB_CHECK(n_out > 0 && n_src0 > 0 && n_src0 < (1ll << 31) && n_src1 < (1ll << 31), "osb_conv_fwd_tc: bad row counts");
+  OSB_CHECK(cout % 32 == 0 && cout > 0, "osb_conv_fwd_tc: cout (%d) must be a multiple of 32", cout);
+  OSB_CHECK(out_split || out_f32, "osb_conv_fwd_tc: no output given");
+  const int cin = c0 + c1;
+  const int cp = cout_pad_of(cout);
+  ConvTcParams p{};
+  p.nt = cp <= 256 ? cp : 256;
+  const int stage_bytes = TC_A_BYTES + p.nt * 128;
+  const int aux_bytes = K * TC_M * 4 + 2 * 256 * 4 + 17 * 8 + 64;
+  int stages = (g_tc_smem_budget - 1024 - aux_bytes) / stage_bytes;      // two CTAs per SM if that leaves >= 3 stages
+  if (stages < 3) stages = (226 * 1024 - 1024 - aux_bytes) / stage_bytes;
+  stages = std::max(2, std::min(8, stages));
+  const size_t smem_bytes = (size_t)stages * stage_bytes + aux_bytes + 1024;
+  OSB_CHECK(smem_bytes <= 227 * 1024, "osb_conv_fwd_tc: tile does not fit in shared memory");
+  int tmem_cols = 32;
+  while (tmem_cols < p.nt) tmem_cols <<= 1;
+
+  CUtensorMap tmA0, tmA1, tmB;
+  if (make_tmap(&tmA0, src0, 2ull * c0, (uint64_t)n_src0, 1)) return 1;
+  if (c1) { if (make_tmap(&tmA1, src1, 2ull * c1, (uint64_t)n_src1, 1)) return 1; }
+  else tmA1 = tmA0;
+  if (make_tmap(&tmB, wpack, 2ull * cin, (uint64_t)K * cp, (uint32_t)p.nt)) return 1;
+
+  p.nbr = nbr; p.n_out = n_out; p.K = K; p.nb0 = c0 / 32; p.nb1 = c1 / 32;
+  p.n_src0 = (int)n_src0; p.n_src1 = (int)n_src1;
+  p.cout = cout; p.cout_pad = cp; p.stages = stages; p.tmem_cols = tmem_cols;
+  p.scale = scale; p.shift = shift; p.res = (const uint8_t *)res; p.relu = relu;
+  p.out_split = (uint8_t *)out_split; p.out_f32 = out_f32; p.out_row_map = out_row_map;
+  p.use_gather4 = g_tc_use_gather4;
+
+  static size_t configured = 0;
+  if (smem_bytes > configured) {
+    OSB_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = 227 * 1024;
+  }
+  dim3 grid((unsigned)ceil_div(n_out, TC_M), (unsigned)(cp / p.nt));
+  k_conv_tc<<<grid, TC_THREADS, smem_bytes, stream>>>(tmA0, tmA1, tmB, p);
+  OSB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"
