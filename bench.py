@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""Benchmark of the OpenScene hot path on B200: MinkUNet34C forward + 768-d cosine matching.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+    python bench.py --impl reference ...                     CPU restatement of the reference path (oracle/)
+
+A step = one synthetic ScanNet-shaped scene (BASELINE.json configs[1]: ~200k voxels) through
+  coordinate hashing + stride sets + kernel maps  ->  MinkUNet34C forward (768-d head)  ->
+  per-point L2-normalise + [N,768]x[768,20] cosine scores + argmax.
+`value`  : voxels/s with coords/feats already in HBM (whole job, all ranks).
+`e2e`    : same metric through the public API with pinned HOST buffers: H2D of coords/feats and D2H of the labels
+           inside the timed region.
+Scenes shard one per GPU with no data-path collective (weak scaling); timing = CUDA events, max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='osb200', choices=['osb200', 'reference'])
+    ap.add_argument('--workload', default='config2_200k')
+    ap.add_argument('--arch', default='MinkUNet34C')
+    ap.add_argument('--k-text', type=int, default=20)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--modules', action='store_true', help='time the module-by-module MinkowskiEngine surface instead of the fused engine')
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md 'clocks' line)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+                                          '-i', str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            f = [x.strip() for x in r.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def algorithmic_bytes(census):
+    """per conv 4*N_in*Cin + 4*N_out*Cout + 4*K*Cin*Cout + 8*pairs."""
+    total, flops = 0, 0
+    for (name, pairs, cin, cout, n_in, n_out, K) in census:
+        pairs = pairs if pairs is not None else 0
+        total += 4 * n_in * cin + 4 * n_out * cout + 4 * K * cin * cout + 8 * pairs
+        flops += 2 * pairs * cin * cout
+    return total, flops
+
+
+def crop_sample(coords, target):
+    """Bounded CPU sample of the workload: the x-slab of the scene holding ~target voxels."""
+    if len(coords) <= target:
+        return coords
+    xs = np.sort(coords[:, 1])
+    cut = xs[target]
+    return coords[coords[:, 1] < cut]
+
+
+def cpu_pass(coords, arch, k_text, threads):
+    """One pass of the CPU restatement (oracle/) over `coords`: map building + forward + cosine matching."""
+    from openscene_b200 import minkunet, synth
+    from oracle import matching as om
+    from oracle import me_cpu
+    torch.set_num_threads(threads)
+    model = cpu_pass.cache.get(arch)
+    if model is None:
+        model = synth.build_model(arch, 768, seed=0, ME=minkunet.oracle_me()).eval()
+        cpu_pass.cache[arch] = model
+    text = torch.from_numpy(synth.text_embeddings(k_text))
+    feats = torch.ones(len(coords), 3)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        out = model(me_cpu.SparseTensor(feats, torch.from_numpy(coords)))
+        s = om._hmm(om._l2n(out), text)
+        s.max(1)
+    return time.perf_counter() - t0
+
+
+cpu_pass.cache = {}
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args, rank):
+    """`--impl reference`: the reference's CPU path for this metric.  MinkowskiEngine itself is not installable
+    offline, so this times oracle/ -- the PyTorch-CPU restatement of the same algorithm -- on a bounded
+    sample per step, all host threads."""
+    if rank != 0:
+        return
+    from openscene_b200 import synth
+    coords = crop_sample(synth.scene(args.workload), 25_000)
+    threads = host_threads()
+    for _ in range(args.warmup):
+        cpu_pass(coords, args.arch, args.k_text, threads)
+    ts = [cpu_pass(coords, args.arch, args.k_text, threads) for _ in range(args.steps)]
+    tot = sum(ts)
+    value = len(coords) * args.steps / tot
+    line = {'impl': 'reference', 'metric': 'voxels/s MinkUNet34C fwd + 768-d cosine-sim', 'value': value, 'unit': 'voxels/s',
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * tot / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': f'{args.workload} ({args.arch}, 768-d head, K_text={args.k_text})',
+                       'note': 'CPU restatement of gather-GEMM-scatter (oracle/), not MinkowskiEngine itself'},
+            'cpu_baseline': {'value': value, 'unit': 'voxels/s', 'cores': threads, 'kind': 'port',
+                             'sample': f'x-slab crop of {args.workload}: {len(coords)} voxels per step'},
+            'e2e': {'value': value, 'unit': 'voxels/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get('RANK', 0))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    if args.impl == 'reference':
+        return run_reference(args, rank)
+
+    import torch.distributed as dist
+    from openscene_b200 import _cabi, engine, matching, synth, tc
+    from openscene_b200 import me as ME
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    # ---- workload: one scene per rank (weak scaling), seeded by rank ---------------------------------
+    coords_np = synth.scene(args.workload, seed=rank)
+    n0 = len(coords_np)
+    coords_host = torch.from_numpy(coords_np).pin_memory()
+    feats_host = torch.ones(n0, 3).pin_memory()                      # dataset/feature_loader.py:184
+    coords_dev, feats_dev = coords_host.to(dev), feats_host.to(dev)
+    text = torch.from_numpy(synth.text_embeddings(args.k_text)).to(dev)
+    model = synth.build_model(args.arch, 768, seed=0).eval().to(dev)
+    eng = engine.FusedMinkUNet(model)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def step_device():
+        if args.modules:
+            out = model(ME.SparseTensor(feats_dev, coords_dev))
+        else:
+            out = eng(coords_dev, feats_dev)
+        return matching._scores(out, None, text, normalize=True)
+
+    def step_e2e():
+        c = coords_host.to(dev, non_blocking=True)
+        f = feats_host.to(dev, non_blocking=True)
+        out = model(ME.SparseTensor(f, c)) if args.modules else eng(c, f)
+        _, label, _ = matching._scores(out, None, text, normalize=True)
+        return label.cpu()
+
+    def timed(fn, k):
+        evs = []
+        for _ in range(k):
+            flush.zero_()                                            # L2 flush, outside the timed events
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = _cabi.lib().osb_launch_count()
+    ms_dev = timed(step_device, args.steps)
+    launches = _cabi.lib().osb_launch_count() - l0
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    ms_e2e = timed(step_e2e, args.steps)
+    barrier()
+
+    # ---- dominant kernel (k_conv_tc) timed live with CUDA events on the launching stream -------------
+    conv_ms, conv_calls = 0.0, 0
+    if not args.modules:
+        orig = tc.conv_tc
+        pend = []
+
+        def hooked(*a, **kw):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); r = orig(*a, **kw); e1.record()
+            pend.append((e0, e1))
+            return r
+        tc.conv_tc = hooked
+        engine.tc.conv_tc = hooked
+        reps = 3
+        for _ in range(reps):
+            flush.zero_()
+            step_device()
+        torch.cuda.synchronize()
+        tc.conv_tc = orig
+        engine.tc.conv_tc = orig
+        conv_ms = sum(a.elapsed_time(b) for a, b in pend) / reps
+        conv_calls = len(pend) // reps
+        census = eng.conv_census(eng.last_cm)
+        tc_rows = [r for r in census if r[0] != 'stem']
+        conv_bytes, conv_flops = algorithmic_bytes(tc_rows)
+        all_bytes, all_flops = algorithmic_bytes(census)
+
+    # ---- gather over ranks: max time, sum of voxels -----------------------------------------------
+    stats = torch.tensor([ms_dev, ms_e2e, float(n0)], dtype=torch.float64, device=dev)
+    if world > 1:
+        allst = [torch.zeros_like(stats) for _ in range(world)]
+        dist.all_gather(allst, stats)
+        allst = torch.stack(allst).cpu()
+    else:
+        allst = stats.cpu().unsqueeze(0)
+    t_dev, t_e2e, total_vox = float(allst[:, 0].max()), float(allst[:, 1].max()), float(allst[:, 2].sum())
+    if rank == 0:
+        peak, peak_src = peaks()
+        line = {
+            'metric': 'voxels/s MinkUNet34C fwd + 768-d cosine-sim', 'value': total_vox * args.steps / (t_dev / 1e3),
+            'unit': 'voxels/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': t_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'bf16x3 (split fp32 operands, fp32 accumulate)', 'data': 'synthetic',
+            'config': {'workload': f'{args.workload}: {n0} voxels/scene, one scene per GPU, {args.arch}, 768-d head, '
+                                   f'K_text={args.k_text}, cosine (L2-normalised) scores + argmax',
+                       'path': 'module surface' if args.modules else 'fused engine', 'l2': 'flushed (256 MiB memset) before every timed step',
+                       'points': 'stride-1 voxels fed to SparseTensor'},
+            'e2e': {'value': total_vox * args.steps / (t_e2e / 1e3), 'unit': 'voxels/s', 'ms_per_step': t_e2e / args.steps,
+                    'h2d_bytes_per_step': int(coords_host.numel() * 4 + feats_host.numel() * 4), 'd2h_bytes_per_step': int(n0 * 8)},
+            'gpu_launches': int(launches), 'clocks': clocks,
+        }
+        if not args.modules:
+            ach = conv_bytes / (conv_ms * 1e-3) / 1e9
+            line['roofline'] = {'bound': 'hbm', 'kernel': 'k_conv_tc', 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
+                                'frac': ach / peak, 'traffic': None, 'peak_source': peak_src,
+                                'launches_per_step': conv_calls, 'kernel_ms_per_step': conv_ms,
+                                'algorithmic_bytes_per_step': conv_bytes, 'tflops': conv_flops / (conv_ms * 1e-3) / 1e12,
+                                'step_algorithmic_bytes': all_bytes, 'step_gflop': all_flops / 1e9}
+        if world == 1 and not args.no_cpu_baseline:
+            sample = crop_sample(coords_np, 50_000)
+            threads = host_threads()
+            dt = cpu_pass(sample, args.arch, args.k_text, threads)
+            line['cpu_baseline'] = {'value': len(sample) / dt, 'unit': 'voxels/s', 'cores': threads, 'kind': 'port',
+                                    'sample': f'x-slab crop of the same scene: {len(sample)} voxels, one pass, {dt:.1f} s',
+                                    'note': 'PyTorch-CPU restatement of gather-GEMM-scatter (oracle/), not MinkowskiEngine'}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

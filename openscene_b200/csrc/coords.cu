@@ -226,7 +226,6 @@ int osb_coordset_build(const int32_t *coords, int64_t n, int32_t *coords_int, in
   k_morton_from_coords<<<nb, 256, 0, stream>>>((const int4 *)coords, n, 1, morton, idx, status);
   OSB_LAUNCH_CHECK();
   OSB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, sort_bytes, morton, morton_s, idx, perm, (int)n, 0, 64, stream));
-  count_launch(4);
   k_permute_coords<<<nb, 256, 0, stream>>>((const int4 *)coords, perm, morton_s, n, (int4 *)coords_int, inv_perm, status);
   OSB_LAUNCH_CHECK();
   if (osb_hash_build(coords_int, n, slots, cap, stream_)) return 1;
@@ -255,11 +254,9 @@ int osb_coordset_stride(const int32_t *coords_fine, int64_t n, int32_t new_ts, i
   k_morton_from_coords<<<nb, 256, 0, stream>>>((const int4 *)coords_fine, n, new_ts, key, idx, status);
   OSB_LAUNCH_CHECK();
   OSB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, sort_bytes, key, key_s, idx, order, (int)n, 0, 64, stream));
-  count_launch(4);
   k_run_heads<<<nb, 256, 0, stream>>>(key_s, n, heads);
   OSB_LAUNCH_CHECK();
   OSB_CUDA(cub::DeviceScan::InclusiveSum(cub_tmp, scan_bytes, heads, ids, (int)n, stream));
-  count_launch(2);
   k_emit_coarse<<<nb, 256, 0, stream>>>((const int4 *)coords_fine, order, heads, ids, n, new_ts, (int4 *)coords_coarse,
                                         parent_of);
   OSB_LAUNCH_CHECK();

@@ -141,12 +141,10 @@ int osb_voxelize(const void *coords, int32_t coords_is_f64, int64_t n, const dou
   OSB_LAUNCH_CHECK();
   size_t tb = tmp_bytes;
   OSB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, key, key_s, idx, idx_s, (int)n, 0, 64, stream));
-  count_launch(8);
   k_vox_heads<<<nb, 256, 0, stream>>>(key_s, n, heads);
   OSB_LAUNCH_CHECK();
   tb = tmp_bytes;
   OSB_CUDA(cub::DeviceScan::InclusiveSum(tmp, tb, heads, ids, (int)n, stream));
-  count_launch(2);
   k_vox_emit<<<nb, 256, 0, stream>>>(idx_s, heads, ids, c32, n, coords_vox, inds, inds_reverse);
   OSB_LAUNCH_CHECK();
   int32_t last = 0;
