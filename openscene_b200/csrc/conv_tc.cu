@@ -13,8 +13,10 @@
 // One CTA = 128 output rows x NT output channels.  A pipeline stage holds one (offset k, 32-channel
 // block) pair: A = 128 gathered rows x 128 B (TMA tile::gather4, 128B swizzle, missing neighbours are
 // out-of-bounds rows -> hardware zero fill, no L2 traffic), B = NT weight rows x 128 B.
-// Warp roles: 0 = TMA producer (every lane issues one gather4), 1 = TMEM alloc + MMA issuer,
-// 2..5 = epilogue (TMEM -> registers -> affine/residual/ReLU -> split-bf16 or fp32 rows).
+// Warp roles: 0 = TMA producer of the weight tiles, 1 = TMEM alloc + MMA issuer, 2..5 = TMA gather4
+// producers for 32 rows each during the main loop (one elected lane issues 8 gathers per stage; a
+// single warp issuing all 32 is serialised through uniform registers and costs ~1.5 us per stage),
+// then the epilogue (TMEM -> registers -> affine/residual/ReLU -> split-bf16 or fp32 rows).
 #include "common.cuh"
 
 #include <cuda.h>
@@ -64,6 +66,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     if (it > (1u << 26)) __trap();   // a lost TMA / MMA completion must not hang the GPU
   }
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int col, int r0, int r1,
                                             int r2, int r3) {
@@ -158,35 +165,19 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
   const int nb = p.nb0 + p.nb1;
 
   if (warp == 0) {
-    // ================================ TMA producer =================================
+    // ============================ TMA producer: weight tiles =========================
     int s = 0;
     uint32_t phase = 0;
     for (uint32_t km = kmask; km; km &= km - 1) {
       const int k = __ffs(km) - 1;
-      const int4 rows = *reinterpret_cast<const int4 *>(s_nbr + k * TC_M + 4 * lane);
       for (int cb = 0; cb < nb; ++cb) {
         mbar_wait(empty0 + 8 * s, phase ^ 1);
-        const uint32_t a_dst = smem_u32(smem + s * stage_bytes);
-        const uint32_t fb = full0 + 8 * s;
-        if (lane == 0) {
-          mbar_expect_tx(fb, (uint32_t)stage_bytes);
-          tma_load_2d(a_dst + TC_A_BYTES, &tmB, fb, cb * 64, k * p.cout_pad + n0);
+        if (elect_one()) {
+          const uint32_t fb = full0 + 8 * s;
+          mbar_expect_tx(fb, (uint32_t)stage_bytes);      // A (4 warps x 8 gathers) + B bytes of this stage
+          tma_load_2d(smem_u32(smem + s * stage_bytes) + TC_A_BYTES, &tmB, fb, cb * 64, k * p.cout_pad + n0);
         }
         __syncwarp();
-        const bool first = cb < p.nb0;
-        const CUtensorMap *tm = first ? &tmA0 : &tmA1;
-        const int col = (first ? cb : cb - p.nb0) * 64;
-        const int oob = first ? p.n_src0 : p.n_src1;           // one past the last row: zero fill
-        const int r0 = rows.x >= 0 ? rows.x : oob, r1 = rows.y >= 0 ? rows.y : oob;
-        const int r2 = rows.z >= 0 ? rows.z : oob, r3 = rows.w >= 0 ? rows.w : oob;
-        if (p.use_gather4) {
-          tma_gather4(a_dst + lane * 512, tm, fb, col, r0, r1, r2, r3);
-        } else {   // same tensor map, one row per copy (debug / cross-check path)
-          tma_load_2d(a_dst + lane * 512, tm, fb, col, r0);
-          tma_load_2d(a_dst + lane * 512 + 128, tm, fb, col, r1);
-          tma_load_2d(a_dst + lane * 512 + 256, tm, fb, col, r2);
-          tma_load_2d(a_dst + lane * 512 + 384, tm, fb, col, r3);
-        }
         if (++s == p.stages) { s = 0; phase ^= 1; }
       }
     }
@@ -200,27 +191,63 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
       for (int cb = 0; cb < nb; ++cb) {
         mbar_wait(full0 + 8 * s, phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
           const uint64_t da = umma_desc(a_addr), db = umma_desc(a_addr + TC_A_BYTES);
           // 128-byte line = [hi ch0-15 | hi ch16-31 | lo ch0-15 | lo ch16-31]; +2 per 32-byte K slice
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            umma_bf16(tmem_base, da + 2 * h, db + 2 * h, idesc, acc);       // hi * Whi
-            acc = 1;
+            umma_bf16(tmem_base, da + 2 * h, db + 2 * h, idesc, (h == 0) ? acc : 1u);   // hi * Whi
             umma_bf16(tmem_base, da + 2 * h, db + 2 * h + 4, idesc, 1);     // hi * Wlo
             umma_bf16(tmem_base, da + 2 * h + 4, db + 2 * h, idesc, 1);     // lo * Whi
           }
           umma_commit(empty0 + 8 * s);      // frees the stage when these MMAs retire
         }
+        acc = 1;
         __syncwarp();
         if (++s == p.stages) { s = 0; phase ^= 1; }
       }
     }
-    if (lane == 0) umma_commit(accum_bar);
+    if (elect_one()) umma_commit(accum_bar);
     __syncwarp();
   } else {
-    // ================================ epilogue ======================================
+    // ================= A producers (32 rows per warp), then epilogue ====================
+    {
+      const int w = warp - 2;                     // rows [32w, 32w+32) of the tile
+      int s = 0;
+      uint32_t phase = 0;
+      for (uint32_t km = kmask; km; km &= km - 1) {
+        const int k = __ffs(km) - 1;
+        const int32_t *rows = s_nbr + k * TC_M + w * 32;
+        for (int cb = 0; cb < nb; ++cb) {
+          mbar_wait(empty0 + 8 * s, phase ^ 1);
+          if (elect_one()) {
+            const uint32_t a_dst = smem_u32(smem + s * stage_bytes) + w * 4096;
+            const uint32_t fb = full0 + 8 * s;
+            const bool first = cb < p.nb0;
+            const CUtensorMap *tm = first ? &tmA0 : &tmA1;
+            const int col = (first ? cb : cb - p.nb0) * 64;
+            const int oob = first ? p.n_src0 : p.n_src1;       // one past the last row: hardware zero fill
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int4 r4 = *reinterpret_cast<const int4 *>(rows + 4 * j);
+              const int r0 = r4.x >= 0 ? r4.x : oob, r1 = r4.y >= 0 ? r4.y : oob;
+              const int r2 = r4.z >= 0 ? r4.z : oob, r3 = r4.w >= 0 ? r4.w : oob;
+              if (p.use_gather4) {
+                tma_gather4(a_dst + j * 512, tm, fb, col, r0, r1, r2, r3);
+              } else {   // same tensor map, one row per copy (debug / cross-check path)
+                tma_load_2d(a_dst + j * 512, tm, fb, col, r0);
+                tma_load_2d(a_dst + j * 512 + 128, tm, fb, col, r1);
+                tma_load_2d(a_dst + j * 512 + 256, tm, fb, col, r2);
+                tma_load_2d(a_dst + j * 512 + 384, tm, fb, col, r3);
+              }
+            }
+          }
+          __syncwarp();
+          if (++s == p.stages) { s = 0; phase ^= 1; }
+        }
+      }
+    }
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int m = q * 32 + lane;
     const int64_t o = row0 + m;
