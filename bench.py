@@ -136,10 +136,13 @@ cpu_pass.cache = {}
 
 
 def host_threads():
+    """Threads for the CPU arm: every core the process may use, capped at 64 (beyond that the many small
+    per-offset GEMMs of the gather-GEMM-scatter algorithm slow down from oversubscription)."""
     try:
-        return len(os.sched_getaffinity(0))
+        n = len(os.sched_getaffinity(0))
     except Exception:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    return max(1, min(n, int(os.environ.get('OSB_CPU_THREADS', 64))))
 
 
 def run_reference(args, rank):
@@ -299,7 +302,7 @@ def main():
                                 'algorithmic_bytes_per_step': conv_bytes, 'tflops': conv_flops / (conv_ms * 1e-3) / 1e12,
                                 'step_algorithmic_bytes': all_bytes, 'step_gflop': all_flops / 1e9}
         if world == 1 and not args.no_cpu_baseline:
-            sample = crop_sample(coords_np, 50_000)
+            sample = crop_sample(coords_np, 25_000)
             threads = host_threads()
             dt = cpu_pass(sample, args.arch, args.k_text, threads)
             line['cpu_baseline'] = {'value': len(sample) / dt, 'unit': 'voxels/s', 'cores': threads, 'kind': 'port',

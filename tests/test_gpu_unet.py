@@ -28,25 +28,35 @@ def test_forward_matches_reference_golden(arch):
 
 
 def test_train_mode_batchnorm_and_backward_match_oracle():
-    """distill.py runs the net in train mode (BN batch statistics) and back-propagates a cosine loss."""
+    """distill.py runs the net in train mode (BN batch statistics) and back-propagates a cosine loss.
+    Truth = fp64 oracle; yardstick = the fp32 oracle (reference precision): train-mode BN over the few
+    voxels of the coarse levels is ill-conditioned, so the GPU error is bounded by a multiple of it."""
     from openscene_b200 import me, minkunet
     from oracle import matching as omatch
     from oracle import me_cpu
     c = synth.random_cloud(1500, 20, seed=8, batch=2)
     f = torch.rand(len(c), 3, generator=torch.Generator().manual_seed(0))
     tgt = torch.randn(len(c), 64, generator=torch.Generator().manual_seed(1))
-    mo = synth.build_model('MinkUNet14A', 64, seed=0, ME=minkunet.oracle_me()).double().train()
+    m64 = synth.build_model('MinkUNet14A', 64, seed=0, ME=minkunet.oracle_me()).double().train()
+    m32 = synth.build_model('MinkUNet14A', 64, seed=0, ME=minkunet.oracle_me()).train()
     mg = synth.build_model('MinkUNet14A', 64, seed=0).to(DEV).train()
-    oo = mo(me_cpu.SparseTensor(f.double(), torch.from_numpy(c)))
+    o64 = m64(me_cpu.SparseTensor(f.double(), torch.from_numpy(c)))
+    o32 = m32(me_cpu.SparseTensor(f, torch.from_numpy(c)))
     og = mg(me.SparseTensor(f.to(DEV), torch.from_numpy(c).to(DEV)))
-    assert rel_row_err(og.detach().cpu().numpy(), oo.detach().numpy()) < TOL
-    lo = omatch.distill_loss(oo, tgt.double())
+    assert rel_row_err(og.detach().cpu().numpy(), o64.detach().numpy()) < TOL
+    l64 = omatch.distill_loss(o64, tgt.double())
+    l32 = omatch.distill_loss(o32, tgt)
     lg = (1 - torch.nn.CosineSimilarity()(og, tgt.to(DEV))).mean()
-    assert abs(lo.item() - lg.item()) < 1e-5
-    lo.backward()
-    lg.backward()
-    for (n, po), (_, pg) in zip(mo.named_parameters(), mg.named_parameters()):
-        a, b = po.grad.numpy(), pg.grad.cpu().numpy()
-        assert np.abs(a - b).max() <= 1e-2 * np.abs(a).max() + 1e-9, n   # fp32 GPU vs fp64 oracle through train-mode BN
+    assert abs(l64.item() - lg.item()) < 1e-5
+    l64.backward(); l32.backward(); lg.backward()
+    worst = 0.0
+    for (n, p64), (_, p32), (_, pg) in zip(m64.named_parameters(), m32.named_parameters(), mg.named_parameters()):
+        a = p64.grad.numpy()
+        e_ref = np.abs(a - p32.grad.numpy().astype(np.float64)).max()
+        e_gpu = np.abs(a - pg.grad.cpu().numpy().astype(np.float64)).max()
+        scale = np.abs(a).max()
+        worst = max(worst, e_gpu / scale)
+        assert e_gpu <= 8 * e_ref + 1e-4 * scale, (n, e_gpu, e_ref, scale)
+    assert worst < 5e-2
     # running statistics were updated identically
-    assert torch.allclose(mo.bn0.bn.running_mean.float(), mg.bn0.bn.running_mean.cpu(), atol=1e-5)
+    assert torch.allclose(m64.bn0.bn.running_mean.float(), mg.bn0.bn.running_mean.cpu(), atol=1e-5)
