@@ -57,7 +57,7 @@ class ClockSampler:
     def __init__(self, index):
         self.rows, self.proc = [], None
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '200',
                                           '-i', str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -228,10 +228,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local) if rank == 0 else None     # started before warm-up: nvidia-smi start-up stalls the GPU briefly
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        time.sleep(1.5)
+        sampler.rows.clear()
     l0 = _cabi.lib().osb_launch_count()
     ms_dev = timed(step_device, args.steps)
     launches = _cabi.lib().osb_launch_count() - l0

@@ -124,12 +124,15 @@ int osb_conv_wgrad_f32(const float *in, const int32_t *nbr, int64_t n_out, int32
  *               row o is written to out_f32[out_row_map[o]]
  */
 size_t osb_conv_packed_weight_bytes(int32_t K, int32_t cin, int32_t cout);
+/* Scratch osb_conv_fwd_tc needs for this shape: small problems are split over the (offset, channel-block)
+ * sequence across CTAs (fp32 partials + a deterministic reduce kernel); 0 when no split is used. */
+size_t osb_conv_tc_workspace_bytes(int64_t n_out, int32_t K, int32_t cin, int32_t cout);
 int osb_conv_pack_weights(const float *w, int32_t K, int32_t cin, int32_t cout, int32_t transpose_w,
                           void *wpack, void *stream);
 int osb_conv_fwd_tc(const void *src0, int32_t c0, int64_t n_src0, const void *src1, int32_t c1, int64_t n_src1,
                     const int32_t *nbr, int64_t n_out, int32_t K, const void *wpack, int32_t cout,
                     const float *scale, const float *shift, const void *res, int32_t relu, void *out_split,
-                    float *out_f32, const int32_t *out_row_map, void *stream);
+                    float *out_f32, const int32_t *out_row_map, void *ws, size_t ws_bytes, void *stream);
 
 /* Stem: fused kernel-map probe + conv for tiny cin (<= 4), fp32 FMA.  One launch replaces the
  * 5x5x5 map build (125 probes / voxel) and the 3->32 convolution of `conv0p1s1`.

@@ -43,6 +43,9 @@ struct ConvTcParams {
   float *out_f32;
   const int32_t *out_row_map;
   int use_gather4;
+  int nsplit;            // > 1: blockIdx.z handles a contiguous chunk of the (offset, channel-block) stage sequence
+  float *partial;        // [nsplit][n_out][cout_pad] raw accumulators (nsplit > 1)
+  int dbg_skip;          // tuning only: bit0 = do not issue A gathers, bit1 = do not issue B loads
 };
 
 // ------------------------------------------------------------------------------------ PTX helpers
@@ -163,19 +166,34 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
   const uint32_t tmem_base = s_misc[0];
   const uint32_t kmask = s_misc[1];
   const int nb = p.nb0 + p.nb1;
+  // stage sequence of this tile = (valid offsets in ascending k) x (channel blocks); split mode takes a chunk
+  const int n_stage_all = __popc(kmask) * nb;
+  int t_begin = 0, t_end = n_stage_all;
+  if (p.nsplit > 1) {
+    const int per = (n_stage_all + p.nsplit - 1) / p.nsplit;
+    t_begin = min((int)blockIdx.z * per, n_stage_all);
+    t_end = min(t_begin + per, n_stage_all);
+  }
+  const bool have_work = t_end > t_begin;
 
   if (warp == 0) {
     // ============================ TMA producer: weight tiles =========================
     int s = 0;
     uint32_t phase = 0;
+    int t = 0;
     for (uint32_t km = kmask; km; km &= km - 1) {
       const int k = __ffs(km) - 1;
-      for (int cb = 0; cb < nb; ++cb) {
+      for (int cb = 0; cb < nb; ++cb, ++t) {
+        if (t < t_begin || t >= t_end) continue;
         mbar_wait(empty0 + 8 * s, phase ^ 1);
         if (elect_one()) {
           const uint32_t fb = full0 + 8 * s;
-          mbar_expect_tx(fb, (uint32_t)stage_bytes);      // A (4 warps x 8 gathers) + B bytes of this stage
-          tma_load_2d(smem_u32(smem + s * stage_bytes) + TC_A_BYTES, &tmB, fb, cb * 64, k * p.cout_pad + n0);
+          uint32_t bytes = (uint32_t)stage_bytes;        // A (4 warps x 8 gathers) + B bytes of this stage
+          if (p.dbg_skip & 1) bytes -= TC_A_BYTES;
+          if (p.dbg_skip & 2) bytes -= p.nt * 128;
+          mbar_expect_tx(fb, bytes);
+          if (!(p.dbg_skip & 2))
+            tma_load_2d(smem_u32(smem + s * stage_bytes) + TC_A_BYTES, &tmB, fb, cb * 64, k * p.cout_pad + n0);
         }
         __syncwarp();
         if (++s == p.stages) { s = 0; phase ^= 1; }
@@ -187,8 +205,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.nt >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
     int s = 0;
     uint32_t phase = 0, acc = 0;
-    for (uint32_t km = kmask; km; km &= km - 1) {
-      for (int cb = 0; cb < nb; ++cb) {
+    for (int t = t_begin; t < t_end; ++t) {
+      {
         mbar_wait(full0 + 8 * s, phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (elect_one()) {
@@ -216,12 +234,14 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
       const int w = warp - 2;                     // rows [32w, 32w+32) of the tile
       int s = 0;
       uint32_t phase = 0;
+      int t = 0;
       for (uint32_t km = kmask; km; km &= km - 1) {
         const int k = __ffs(km) - 1;
         const int32_t *rows = s_nbr + k * TC_M + w * 32;
-        for (int cb = 0; cb < nb; ++cb) {
+        for (int cb = 0; cb < nb; ++cb, ++t) {
+          if (t < t_begin || t >= t_end) continue;
           mbar_wait(empty0 + 8 * s, phase ^ 1);
-          if (elect_one()) {
+          if (elect_one() && !(p.dbg_skip & 1)) {
             const uint32_t a_dst = smem_u32(smem + s * stage_bytes) + w * 4096;
             const uint32_t fb = full0 + 8 * s;
             const bool first = cb < p.nb0;
@@ -251,7 +271,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int m = q * 32 + lane;
     const int64_t o = row0 + m;
-    if (kmask) {
+    if (have_work) {
       mbar_wait(accum_bar, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
@@ -259,7 +279,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
     const int64_t orow = (live && p.out_row_map) ? (int64_t)__ldg(p.out_row_map + o) : o;
     for (int cbo = 0; cbo < p.nt / 32; ++cbo) {
       float y[32];
-      if (kmask) {
+      if (have_work) {
         uint32_t v0[16], v1[16];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + cbo * 32;
         tmem_ld16(taddr, v0);
@@ -272,7 +292,14 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
         for (int j = 0; j < 32; ++j) y[j] = 0.f;
       }
       const int c0 = n0 + cbo * 32;              // first output channel of this 32-block
-      if (!live || c0 >= p.cout) continue;
+      if (!live) continue;
+      if (p.nsplit > 1) {                        // raw partial sums; k_conv_finish reduces + applies the epilogue
+        float4 *pp = reinterpret_cast<float4 *>(p.partial + ((int64_t)blockIdx.z * p.n_out + o) * p.cout_pad + c0);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) pp[g] = make_float4(y[4 * g], y[4 * g + 1], y[4 * g + 2], y[4 * g + 3]);
+        continue;
+      }
+      if (c0 >= p.cout) continue;
 #pragma unroll
       for (int j = 0; j < 32; ++j) y[j] = fmaf(y[j], s_scale[cbo * 32 + j], s_shift[cbo * 32 + j]);
       if (p.res) {
@@ -313,6 +340,55 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols));
+  }
+}
+
+// ------------------------------------------------------------------ split-mode finish kernel
+// out = epilogue( sum_z partial[z] ): one thread per (row, 8 channels)
+__global__ void k_conv_finish(const float *__restrict__ partial, int nsplit, int64_t n_out, int cout, int cout_pad,
+                              const float *__restrict__ scale, const float *__restrict__ shift,
+                              const uint8_t *__restrict__ res, int relu, uint8_t *__restrict__ out_split,
+                              float *__restrict__ out_f32, const int32_t *__restrict__ out_row_map) {
+  const int groups = cout / 8;
+  const int64_t total = n_out * groups;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t o = e / groups;
+    const int c0 = (int)(e - o * groups) * 8;
+    float y[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int z = 0; z < nsplit; ++z) {
+      const float4 *pp = reinterpret_cast<const float4 *>(partial + ((int64_t)z * n_out + o) * cout_pad + c0);
+      const float4 a = __ldg(pp), b = __ldg(pp + 1);
+      y[0] += a.x; y[1] += a.y; y[2] += a.z; y[3] += a.w; y[4] += b.x; y[5] += b.y; y[6] += b.z; y[7] += b.w;
+    }
+    if (scale) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = fmaf(y[j], __ldg(scale + c0 + j), __ldg(shift + c0 + j));
+    }
+    const int64_t off = o * (int64_t)cout * 4 + split_off_hi(c0);
+    if (res) {
+      const uint4 hq = __ldg(reinterpret_cast<const uint4 *>(res + off)), lq = __ldg(reinterpret_cast<const uint4 *>(res + off + 64));
+      const __nv_bfloat16 *hh = reinterpret_cast<const __nv_bfloat16 *>(&hq);
+      const __nv_bfloat16 *ll = reinterpret_cast<const __nv_bfloat16 *>(&lq);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] += join_bf16(hh[j], ll[j]);
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = fmaxf(y[j], 0.f);
+    }
+    if (out_split) {
+      __align__(16) __nv_bfloat16 hh[8], ll[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) split_bf16(y[j], hh[j], ll[j]);
+      *reinterpret_cast<uint4 *>(out_split + off) = *reinterpret_cast<const uint4 *>(hh);
+      *reinterpret_cast<uint4 *>(out_split + off + 64) = *reinterpret_cast<const uint4 *>(ll);
+    }
+    if (out_f32) {
+      const int64_t orow = out_row_map ? (int64_t)__ldg(out_row_map + o) : o;
+      float4 *op = reinterpret_cast<float4 *>(out_f32 + orow * cout + c0);
+      op[0] = make_float4(y[0], y[1], y[2], y[3]);
+      op[1] = make_float4(y[4], y[5], y[6], y[7]);
+    }
   }
 }
 
@@ -365,10 +441,15 @@ static int make_tmap(CUtensorMap *tm, const void *base, uint64_t cols_elems, uin
 
 static int g_tc_use_gather4 = 1;
 static int g_tc_smem_budget = 112 * 1024;   // per CTA -> two CTAs per SM
+static int g_tc_dbg_skip = 0;
+static int g_tc_force_split = 0;            // 0 = heuristic, >0 = forced nsplit (1 disables)
+static int g_tc_target_ctas = 296;
 
 }  // namespace osb
 
 using namespace osb;
+
+static inline int cout_pad_of(int cout) { return cout <= 256 ? (cout + 15) / 16 * 16 : (cout + 255) / 256 * 256; }
 
 extern "C" {
 
@@ -377,8 +458,21 @@ void osb_debug_set_tc(int use_gather4, int smem_budget) {
   if (use_gather4 >= 0) g_tc_use_gather4 = use_gather4;
   if (smem_budget > 0) g_tc_smem_budget = smem_budget;
 }
+void osb_debug_set_tc2(int dbg_skip, int force_split, int target_ctas) {
+  if (dbg_skip >= 0) g_tc_dbg_skip = dbg_skip;
+  if (force_split >= 0) g_tc_force_split = force_split;
+  if (target_ctas > 0) g_tc_target_ctas = target_ctas;
+}
 
-static inline int cout_pad_of(int cout) { return cout <= 256 ? (cout + 15) / 16 * 16 : (cout + 255) / 256 * 256; }
+// bytes of caller-provided scratch osb_conv_fwd_tc may need for this shape (0 = none)
+size_t osb_conv_tc_workspace_bytes(int64_t n_out, int32_t K, int32_t cin, int32_t cout) {
+  const int cp = cout_pad_of(cout);
+  const int nt = cp <= 256 ? cp : 256;
+  const int64_t ctas = ceil_div(n_out, TC_M) * (cp / nt);
+  int nsplit = g_tc_force_split > 0 ? g_tc_force_split : (int)(g_tc_target_ctas / ctas);
+  nsplit = std::max(1, std::min(nsplit, std::min(32, K * (cin / 32))));
+  return nsplit > 1 ? (size_t)nsplit * n_out * cp * sizeof(float) : 0;
+}
 
 size_t osb_conv_packed_weight_bytes(int32_t K, int32_t cin, int32_t cout) {
   return (size_t)K * cout_pad_of(cout) * cin * 4;
@@ -399,7 +493,7 @@ int osb_conv_pack_weights(const float *w, int32_t K, int32_t cin, int32_t cout, 
 int osb_conv_fwd_tc(const void *src0, int32_t c0, int64_t n_src0, const void *src1, int32_t c1, int64_t n_src1,
                     const int32_t *nbr, int64_t n_out, int32_t K, const void *wpack, int32_t cout, const float *scale,
                     const float *shift, const void *res, int32_t relu, void *out_split, float *out_f32,
-                    const int32_t *out_row_map, void *stream_) {
+                    const int32_t *out_row_map, void *ws, size_t ws_bytes, void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   OSB_CHECK(src0 && c0 > 0 && c0 % 32 == 0 && c1 >= 0 && c1 % 32 == 0, "osb_conv_fwd_tc: channel counts must be multiples of 32 (c0=%d c1=%d)", c0, c1);
   OSB_CHECK((c1 == 0) == (src1 == nullptr), "osb_conv_fwd_tc: src1 / c1 mismatch");
@@ -434,15 +528,31 @@ int osb_conv_fwd_tc(const void *src0, int32_t c0, int64_t n_src0, const void *sr
   p.scale = scale; p.shift = shift; p.res = (const uint8_t *)res; p.relu = relu;
   p.out_split = (uint8_t *)out_split; p.out_f32 = out_f32; p.out_row_map = out_row_map;
   p.use_gather4 = g_tc_use_gather4;
+  p.dbg_skip = g_tc_dbg_skip;
+  const size_t need = osb_conv_tc_workspace_bytes(n_out, K, cin, cout);
+  p.nsplit = 1;
+  p.partial = nullptr;
+  if (need > 0) {
+    OSB_CHECK(ws != nullptr && ws_bytes >= need, "osb_conv_fwd_tc: workspace of %zu bytes required (got %zu)", need, ws_bytes);
+    p.nsplit = (int)(need / ((size_t)n_out * cp * sizeof(float)));
+    p.partial = (float *)ws;
+  }
 
   static size_t configured = 0;
   if (smem_bytes > configured) {
     OSB_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = 227 * 1024;
   }
-  dim3 grid((unsigned)ceil_div(n_out, TC_M), (unsigned)(cp / p.nt));
+  dim3 grid((unsigned)ceil_div(n_out, TC_M), (unsigned)(cp / p.nt), (unsigned)p.nsplit);
   k_conv_tc<<<grid, TC_THREADS, smem_bytes, stream>>>(tmA0, tmA1, tmB, p);
   OSB_LAUNCH_CHECK();
+  if (p.nsplit > 1) {
+    const int64_t total = n_out * (cout / 8);
+    const unsigned fgrid = (unsigned)std::min<int64_t>(ceil_div(total, 256), 148 * 8);
+    k_conv_finish<<<fgrid, 256, 0, stream>>>(p.partial, p.nsplit, n_out, cout, cp, scale, shift, (const uint8_t *)res, relu,
+                                            (uint8_t *)out_split, out_f32, out_row_map);
+    OSB_LAUNCH_CHECK();
+  }
   return 0;
 }
 

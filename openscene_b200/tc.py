@@ -34,15 +34,29 @@ def pack_weights(w3, transpose_w=False):
     return out
 
 
+_WS = {}
+
+
+def _workspace(dev, nbytes):
+    """Grow-only per-device scratch for split-mode convolutions (stream-ordered reuse)."""
+    w = _WS.get(dev)
+    if w is None or w.numel() < nbytes:
+        w = torch.empty(max(nbytes, 32 << 20), dtype=torch.uint8, device=dev)
+        _WS[dev] = w
+    return w
+
+
 def conv_tc(src0, c0, src1, c1, nbr, n_out, K, wpack, cout, scale=None, shift=None, res=None, relu=False,
             out_split=True, out_f32=False, out_row_map=None):
     """One fused sparse convolution.  Returns (split rows or None, fp32 rows or None)."""
     dev = src0.device
     os_ = torch.empty((n_out, 4 * cout), dtype=torch.uint8, device=dev) if out_split else None
     of_ = torch.empty((n_out, cout), dtype=torch.float32, device=dev) if out_f32 else None
+    ws_bytes = C.lib().osb_conv_tc_workspace_bytes(n_out, K, c0 + c1, cout)
+    ws = _workspace(dev, ws_bytes) if ws_bytes else None
     C.call('osb_conv_fwd_tc', C.ptr(src0), c0, src0.shape[0], C.ptr(src1), c1, 0 if src1 is None else src1.shape[0],
            C.ptr(nbr), n_out, K, C.ptr(wpack), cout, C.ptr(scale), C.ptr(shift), C.ptr(res), int(relu),
-           C.ptr(os_), C.ptr(of_), C.ptr(out_row_map), C.stream_ptr())
+           C.ptr(os_), C.ptr(of_), C.ptr(out_row_map), C.ptr(ws), ws_bytes, C.stream_ptr())
     return os_, of_
 
 
@@ -56,7 +70,10 @@ def conv_stem(x, coords, slots, cap, ks, step, w3, scale=None, shift=None, relu=
     return os_, of_
 
 
-def debug_set_tc(use_gather4=-1, smem_budget=0):
+def debug_set_tc(use_gather4=-1, smem_budget=0, dbg_skip=-1, force_split=-1, target_ctas=0):
     fn = C.lib().osb_debug_set_tc
     fn.restype, fn.argtypes = None, [ctypes.c_int, ctypes.c_int]
     fn(use_gather4, smem_budget)
+    fn2 = C.lib().osb_debug_set_tc2
+    fn2.restype, fn2.argtypes = None, [ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    fn2(dbg_skip, force_split, target_ctas)
