@@ -132,6 +132,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
   const int n0 = blockIdx.y * p.nt;
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + 8), accum_bar = smem_u32(bars + 16);
 
+  if (tid == 32 * 2) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
   if (tid == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
     mbar_init(accum_bar, 1);
@@ -145,15 +150,32 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
   }
   __syncthreads();   // s_misc[1] = 0 visible before the atomics below
 
-  // ---- prologue: neighbour rows of this tile -> smem, bit mask of offsets that touch the tile
-  for (int e = tid; e < p.K * TC_M; e += TC_THREADS) {
-    const int k = e >> 7, m = e & 127;
-    const int64_t o = row0 + m;
-    int32_t idx = -1;
-    if (o < p.n_out) idx = p.nbr ? __ldg(p.nbr + (int64_t)k * p.n_out + o) : (int32_t)o;
-    s_nbr[e] = idx;
-    const bool any = __any_sync(0xffffffffu, idx >= 0);
-    if (any && lane == 0) atomicOr(&s_misc[1], 1u << k);
+  // ---- prologue: neighbour rows of this tile -> smem, bit mask of offsets that touch the tile.
+  // All loads of a thread are issued before any is consumed (22 = ceil(32*128/192) independent loads).
+  {
+    constexpr int PRO = (TC_MAXK * TC_M + TC_THREADS - 1) / TC_THREADS;
+    int32_t idx[PRO];
+    const int total = p.K * TC_M;
+#pragma unroll
+    for (int j = 0; j < PRO; ++j) {
+      const int e = tid + j * TC_THREADS;
+      idx[j] = -1;
+      if (e < total) {
+        const int64_t o = row0 + (e & 127);
+        if (o < p.n_out) idx[j] = p.nbr ? __ldg(p.nbr + (int64_t)(e >> 7) * p.n_out + o) : (int32_t)o;
+      }
+    }
+    uint32_t mymask = 0;
+#pragma unroll
+    for (int j = 0; j < PRO; ++j) {
+      const int e = tid + j * TC_THREADS;
+      if (e < total) {
+        s_nbr[e] = idx[j];
+        if (idx[j] >= 0) mymask |= 1u << (e >> 7);
+      }
+    }
+    mymask = __reduce_or_sync(0xffffffffu, mymask);
+    if (lane == 0 && mymask) atomicOr(&s_misc[1], mymask);
   }
   for (int n = tid; n < p.nt; n += TC_THREADS) {
     const int c = n0 + n;
