@@ -45,6 +45,8 @@ struct ConvTcParams {
   int use_gather4;
   int nsplit;            // > 1: blockIdx.z handles a contiguous chunk of the (offset, channel-block) stage sequence
   float *partial;        // [nsplit][n_out][cout_pad] raw accumulators (nsplit > 1)
+  const uint8_t *src0_ptr, *src1_ptr;   // raw bases (L2 prefetch of a later tile's own rows)
+  int pf_dist;           // tiles ahead to prefetch into L2 (0 = off; only when input rows == output rows)
   int dbg_skip;          // tuning only: bit0 = do not issue A gathers, bit1 = do not issue B loads
 };
 
@@ -200,6 +202,20 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
 
   if (warp == 0) {
     // ============================ TMA producer: weight tiles =========================
+    if (p.pf_dist > 0 && blockIdx.y == 0 && blockIdx.z == 0 && elect_one()) {
+      // Stride-1 convolutions read mostly the rows around their own tile (Morton order): pull the rows of the
+      // tile that will run ~one wave later into L2 now, so its gathers do not wait on compulsory DRAM misses.
+      const int64_t r0 = ((int64_t)blockIdx.x + p.pf_dist) * TC_M;
+      if (r0 < p.n_out) {
+        const int64_t nrows = min((int64_t)TC_M, p.n_out - r0);
+        const uint32_t b0 = (uint32_t)(nrows * p.nb0 * 128);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.src0_ptr + r0 * p.nb0 * 128), "r"(b0) : "memory");
+        if (p.nb1) {
+          const uint32_t b1 = (uint32_t)(nrows * p.nb1 * 128);
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.src1_ptr + r0 * p.nb1 * 128), "r"(b1) : "memory");
+        }
+      }
+    }
     int s = 0;
     uint32_t phase = 0;
     int t = 0;
@@ -466,6 +482,7 @@ static int g_tc_smem_budget = 112 * 1024;   // per CTA -> two CTAs per SM
 static int g_tc_dbg_skip = 0;
 static int g_tc_force_split = 0;            // 0 = heuristic, >0 = forced nsplit (1 disables)
 static int g_tc_target_ctas = 296;
+static int g_tc_pf_dist = 296;
 
 }  // namespace osb
 
@@ -480,6 +497,7 @@ void osb_debug_set_tc(int use_gather4, int smem_budget) {
   if (use_gather4 >= 0) g_tc_use_gather4 = use_gather4;
   if (smem_budget > 0) g_tc_smem_budget = smem_budget;
 }
+void osb_debug_set_tc3(int pf_dist) { g_tc_pf_dist = pf_dist; }
 void osb_debug_set_tc2(int dbg_skip, int force_split, int target_ctas) {
   if (dbg_skip >= 0) g_tc_dbg_skip = dbg_skip;
   if (force_split >= 0) g_tc_force_split = force_split;
@@ -551,6 +569,8 @@ int osb_conv_fwd_tc(const void *src0, int32_t c0, int64_t n_src0, const void *sr
   p.out_split = (uint8_t *)out_split; p.out_f32 = out_f32; p.out_row_map = out_row_map;
   p.use_gather4 = g_tc_use_gather4;
   p.dbg_skip = g_tc_dbg_skip;
+  p.src0_ptr = (const uint8_t *)src0; p.src1_ptr = (const uint8_t *)src1;
+  p.pf_dist = (n_src0 == n_out && (c1 == 0 || n_src1 == n_out) && (K & 1)) ? g_tc_pf_dist : 0;
   const size_t need = osb_conv_tc_workspace_bytes(n_out, K, cin, cout);
   p.nsplit = 1;
   p.partial = nullptr;

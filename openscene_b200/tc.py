@@ -70,10 +70,14 @@ def conv_stem(x, coords, slots, cap, ks, step, w3, scale=None, shift=None, relu=
     return os_, of_
 
 
-def debug_set_tc(use_gather4=-1, smem_budget=0, dbg_skip=-1, force_split=-1, target_ctas=0):
+def debug_set_tc(use_gather4=-1, smem_budget=0, dbg_skip=-1, force_split=-1, target_ctas=0, pf_dist=None):
     fn = C.lib().osb_debug_set_tc
     fn.restype, fn.argtypes = None, [ctypes.c_int, ctypes.c_int]
     fn(use_gather4, smem_budget)
     fn2 = C.lib().osb_debug_set_tc2
     fn2.restype, fn2.argtypes = None, [ctypes.c_int, ctypes.c_int, ctypes.c_int]
     fn2(dbg_skip, force_split, target_ctas)
+    if pf_dist is not None:
+        fn3 = C.lib().osb_debug_set_tc3
+        fn3.restype, fn3.argtypes = None, [ctypes.c_int]
+        fn3(pf_dist)

@@ -18,11 +18,15 @@ for _ in range(4):
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 
+HOT = False
+
+
 def timeit(fn, reps=5):
     fn(); torch.cuda.synchronize()
     tot = 0.0
     for _ in range(reps):
-        flush.zero_()
+        if not HOT:
+            flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); fn(); b.record(); torch.cuda.synchronize()
         tot += a.elapsed_time(b)
@@ -42,11 +46,23 @@ def case(level, cin, cout, ks, label, **dbg):
     tc.debug_set_tc(**dbg)
     f32 = cout > 256
     us = timeit(lambda: tc.conv_tc(x, cin, None, 0, nbr, n, K, w, cout, None, None, None, True, not f32, f32, None))
-    tc.debug_set_tc(use_gather4=1, smem_budget=112 * 1024, dbg_skip=0, force_split=0, target_ctas=296)
+    tc.debug_set_tc(use_gather4=1, smem_budget=112 * 1024, dbg_skip=0, force_split=0, target_ctas=296, pf_dist=296)
     print(f'{label:46s} L{level} n={n:7d} {cin:3d}->{cout:3d} k{ks}  {us:9.1f} us', flush=True)
 
 
 B2, B1 = 112 * 1024, 226 * 1024
+if len(sys.argv) > 2 and sys.argv[2] == 'pf':
+    for hot in (False, True):
+        HOT = hot
+        for pf in (0, 148, 296, 444, 592):
+            case(0, 96, 96, 3, f'hot={hot} pf_dist={pf}', pf_dist=pf)
+        case(0, 96, 96, 3, f'hot={hot} pf 296, 1 CTA/SM', pf_dist=148, smem_budget=B1)
+        case(0, 128, 96, 3, f'hot={hot} 128->96 pf 296', pf_dist=296)
+        case(0, 96, 96, 1, f'hot={hot} 1x1 pf 0', pf_dist=0)
+        case(0, 96, 96, 1, f'hot={hot} 1x1 pf 296', pf_dist=296)
+        case(0, 96, 768, 1, f'hot={hot} final pf 0', pf_dist=0)
+        case(0, 96, 768, 1, f'hot={hot} final pf 296', pf_dist=296)
+    sys.exit(0)
 case(0, 96, 96, 3, 'base (2 CTA/SM, gather4)')
 case(0, 96, 96, 3, '1 CTA/SM deep pipeline', smem_budget=B1)
 case(0, 96, 96, 3, 'row loads instead of gather4', use_gather4=0)
