@@ -134,7 +134,7 @@ int osb_conv_fwd_tc(const void *src0, int32_t c0, int64_t n_src0, const void *sr
                     const float *scale, const float *shift, const void *res, int32_t relu, void *out_split,
                     float *out_f32, const int32_t *out_row_map, void *ws, size_t ws_bytes, void *stream);
 
-/* Stem: fused kernel-map probe + conv for tiny cin (<= 4), fp32 FMA.  One launch replaces the
+/* Stem: fused kernel-map probe + conv for tiny cin (<= 3) and cout <= 32, fp32 FMA.  One launch replaces the
  * 5x5x5 map build (125 probes / voxel) and the 3->32 convolution of `conv0p1s1`.
  *   in  fp32 [n, cin] internal order;  w fp32 [K, cin, cout];  epilogue as osb_conv_fwd_tc. */
 int osb_conv_stem_fused(const float *in, int32_t cin, const int32_t *coords, int64_t n, const void *slots,

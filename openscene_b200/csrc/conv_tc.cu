@@ -13,10 +13,15 @@
 // One CTA = 128 output rows x NT output channels.  A pipeline stage holds one (offset k, 32-channel
 // block) pair: A = 128 gathered rows x 128 B (TMA tile::gather4, 128B swizzle, missing neighbours are
 // out-of-bounds rows -> hardware zero fill, no L2 traffic), B = NT weight rows x 128 B.
-// Warp roles: 0 = TMA producer of the weight tiles, 1 = TMEM alloc + MMA issuer, 2..5 = TMA gather4
-// producers for 32 rows each during the main loop (one elected lane issues 8 gathers per stage; a
-// single warp issuing all 32 is serialised through uniform registers and costs ~1.5 us per stage),
-// then the epilogue (TMEM -> registers -> affine/residual/ReLU -> split-bf16 or fp32 rows).
+// Warp roles: 0 = TMA producer of the weight tiles, 1 = TMEM alloc + MMA issuer, 2..5 = producers of
+// the gathered A rows (32 rows per warp) during the main loop, then the epilogue (TMEM -> registers ->
+// affine/residual/ReLU -> split-bf16 or fp32 rows).
+// Three A paths are kept selectable (osb_debug_set_tc), measured on B200 on the level-0 96->96 3^3 layer:
+//   2 (default) cp.async.cg 16 B x 8 lanes per row, swizzled by hand, completion through
+//               cp.async.mbarrier.arrive.noinc on the stage's full barrier;
+//   1           TMA tile::gather4 (4 rows x 128 B per instruction): the TMA unit spends ~20-25 cycles per
+//               gather4 instruction regardless of bytes (~23 B/clk/SM), which bounds the whole kernel;
+//   0           one TMA row load per row (cross-check path).
 #include "common.cuh"
 
 #include <cuda.h>
@@ -71,6 +76,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     if (it > (1u << 26)) __trap();   // a lost TMA / MMA completion must not hang the GPU
   }
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// this thread's arrival on `bar` fires when all of its prior cp.async have landed (count pre-armed at init)
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -140,7 +152,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
   }
   if (tid == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    const uint32_t full_count = p.use_gather4 == 2 ? 1 + 128 : 1;     // B producer (+ 128 cp.async A producers)
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full0 + 8 * s, full_count); mbar_init(empty0 + 8 * s, 1); }
     mbar_init(accum_bar, 1);
     s_misc[1] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -227,7 +240,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
         if (elect_one()) {
           const uint32_t fb = full0 + 8 * s;
           uint32_t bytes = (uint32_t)stage_bytes;        // A (4 warps x 8 gathers) + B bytes of this stage
-          if (p.dbg_skip & 1) bytes -= TC_A_BYTES;
+          if ((p.dbg_skip & 1) || p.use_gather4 == 2) bytes -= TC_A_BYTES;
           if (p.dbg_skip & 2) bytes -= p.nt * 128;
           mbar_expect_tx(fb, bytes);
           if (!(p.dbg_skip & 2))
@@ -246,6 +259,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
     for (int t = t_begin; t < t_end; ++t) {
       {
         mbar_wait(full0 + 8 * s, phase);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) writes -> UMMA reads
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
@@ -268,7 +282,40 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
     __syncwarp();
   } else {
     // ================= A producers (32 rows per warp), then epilogue ====================
-    {
+    if (p.use_gather4 == 2) {
+      // cp.async producers: 8 lanes cover one 128-byte row line (one L2 line per 8 lanes), 4 rows per warp
+      // instruction, 8 instructions per stage; destination carries the 128B swizzle (chunk ^ (row & 7)).
+      const int w = warp - 2, j = lane & 7, q = lane >> 3;
+      int s = 0;
+      uint32_t phase = 0;
+      int t = 0;
+      for (uint32_t km = kmask; km; km &= km - 1) {
+        const int k = __ffs(km) - 1;
+        int32_t ridx[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ridx[i] = s_nbr[k * TC_M + w * 32 + 4 * i + q];
+        for (int cb = 0; cb < nb; ++cb, ++t) {
+          if (t < t_begin || t >= t_end) continue;
+          mbar_wait(empty0 + 8 * s, phase ^ 1);
+          const bool first = cb < p.nb0;
+          const uint8_t *src = first ? p.src0_ptr : p.src1_ptr;
+          const int64_t row_bytes = (int64_t)(first ? p.nb0 : p.nb1) * 128;
+          const int col_byte = (first ? cb : cb - p.nb0) * 128 + j * 16;
+          const uint32_t a_dst = smem_u32(smem + s * stage_bytes) + (w * 32 + q) * 128;
+          if (!(p.dbg_skip & 1)) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int m7 = (4 * i + q) & 7;
+              const bool valid = ridx[i] >= 0;
+              const uint8_t *sp = valid ? src + (int64_t)ridx[i] * row_bytes + col_byte : src;
+              cp_async16(a_dst + i * 512 + ((j ^ m7) << 4), sp, valid ? 16u : 0u);      // size 0 -> zero fill
+            }
+          }
+          cp_async_arrive_noinc(full0 + 8 * s);
+          if (++s == p.stages) { s = 0; phase ^= 1; }
+        }
+      }
+    } else {
       const int w = warp - 2;                     // rows [32w, 32w+32) of the tile
       int s = 0;
       uint32_t phase = 0;
@@ -477,7 +524,7 @@ static int make_tmap(CUtensorMap *tm, const void *base, uint64_t cols_elems, uin
   return 0;
 }
 
-static int g_tc_use_gather4 = 1;
+static int g_tc_use_gather4 = 2;            // A operand path: 2 = cp.async (default), 1 = TMA gather4, 0 = TMA row loads
 static int g_tc_smem_budget = 112 * 1024;   // per CTA -> two CTAs per SM
 static int g_tc_dbg_skip = 0;
 static int g_tc_force_split = 0;            // 0 = heuristic, >0 = forced nsplit (1 disables)

@@ -53,8 +53,8 @@ class FusedMinkUNet:
         self.device = p.device
         with torch.cuda.device(self.device), torch.no_grad():
             self.stem = _Conv(net.conv0p1s1, net.bn0, keep_f32=True)
-            if self.stem.cin > 8 or self.stem.cout > 64 or self.stem.cout % 32:
-                raise NotImplementedError("fused stem supports cin <= 8, cout in {32, 64}")
+            if self.stem.cin > 3 or self.stem.cout != 32:
+                raise NotImplementedError("fused stem supports cin <= 3, cout == 32 (every MinkUNet: INIT_DIM = 32, 3 input features)")
             self.enc, self.dec = [], []
             for i in range(1, 5):
                 down = _Conv(getattr(net, f'conv{i}p{2 ** (i - 1)}s2'), getattr(net, f'bn{i}'))

@@ -46,7 +46,7 @@ def case(level, cin, cout, ks, label, **dbg):
     tc.debug_set_tc(**dbg)
     f32 = cout > 256
     us = timeit(lambda: tc.conv_tc(x, cin, None, 0, nbr, n, K, w, cout, None, None, None, True, not f32, f32, None))
-    tc.debug_set_tc(use_gather4=1, smem_budget=112 * 1024, dbg_skip=0, force_split=0, target_ctas=296, pf_dist=296)
+    tc.debug_set_tc(use_gather4=2, smem_budget=112 * 1024, dbg_skip=0, force_split=0, target_ctas=296, pf_dist=296)
     print(f'{label:46s} L{level} n={n:7d} {cin:3d}->{cout:3d} k{ks}  {us:9.1f} us', flush=True)
 
 
@@ -63,9 +63,9 @@ if len(sys.argv) > 2 and sys.argv[2] == 'pf':
         case(0, 96, 768, 1, f'hot={hot} final pf 0', pf_dist=0)
         case(0, 96, 768, 1, f'hot={hot} final pf 296', pf_dist=296)
     sys.exit(0)
-case(0, 96, 96, 3, 'base (2 CTA/SM, gather4)')
+case(0, 96, 96, 3, 'base (2 CTA/SM, cp.async)')
+case(0, 96, 96, 3, 'TMA gather4', use_gather4=1)
 case(0, 96, 96, 3, '1 CTA/SM deep pipeline', smem_budget=B1)
-case(0, 96, 96, 3, 'row loads instead of gather4', use_gather4=0)
 case(0, 96, 96, 3, 'no A gathers (timing only)', dbg_skip=1)
 case(0, 96, 96, 3, 'no B loads (timing only)', dbg_skip=2)
 case(0, 96, 96, 3, 'no A, no B (MMA + epilogue only)', dbg_skip=3)

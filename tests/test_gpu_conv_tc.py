@@ -17,7 +17,7 @@ from openscene_b200 import synth, tc
 from openscene_b200.coords import CoordinateManager
 from oracle import me_cpu
 mode, cin0, cin1, cout, ks, stride, epi = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6]), sys.argv[7]
-tc.debug_set_tc(1 if mode == 'gather4' else 0, 0)
+tc.debug_set_tc({'cpasync': 2, 'gather4': 1, 'rows': 0}[mode], 0)
 dev = torch.device('cuda:0')
 c = synth.scene('tiny') if ks != 1 else synth.random_cloud(700, 16, seed=1)
 cm = CoordinateManager(torch.from_numpy(c).to(dev))
@@ -107,12 +107,18 @@ def _run(mode, case):
 
 
 @pytest.mark.parametrize('case', CASES)
+def test_conv_tc_cpasync(case):
+    r = _run('cpasync', case)
+    assert r.returncode == 0 and 'OK' in r.stdout, r.stdout[-500:] + r.stderr[-1500:]
+
+
+@pytest.mark.parametrize('case', CASES[:6])
 def test_conv_tc_gather4(case):
     r = _run('gather4', case)
     assert r.returncode == 0 and 'OK' in r.stdout, r.stdout[-500:] + r.stderr[-1500:]
 
 
-@pytest.mark.parametrize('case', CASES[:3])
+@pytest.mark.parametrize('case', CASES[:2])
 def test_conv_tc_row_loads(case):
     r = _run('rows', case)
     assert r.returncode == 0 and 'OK' in r.stdout, r.stdout[-500:] + r.stderr[-1500:]
