@@ -52,7 +52,8 @@ struct ConvTcParams {
   float *partial;        // [nsplit][n_out][cout_pad] raw accumulators (nsplit > 1)
   const uint8_t *src0_ptr, *src1_ptr;   // raw bases (L2 prefetch of a later tile's own rows)
   int pf_dist;           // tiles ahead to prefetch into L2 (0 = off; only when input rows == output rows)
-  int dbg_skip;          // tuning only: bit0 = do not issue A gathers, bit1 = do not issue B loads
+  int dbg_skip;          // tuning only: bit0 = no A gathers, bit1 = no B loads, bit2 = no main loop, bit3 = no stores
+  long long *dbg_clock;  // tuning only: per-CTA timestamps [gridDim.x][8] (may be NULL)
 };
 
 // ------------------------------------------------------------------------------------ PTX helpers
@@ -142,6 +143,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
   uint32_t *s_misc = reinterpret_cast<uint32_t *>(bars + 17);               // [0] tmem base, [1] kmask
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (p.dbg_clock && tid == 64) { p.dbg_clock[blockIdx.x * 8 + 0] = clock64(); unsigned sm; asm("mov.u32 %0, %%smid;" : "=r"(sm)); p.dbg_clock[blockIdx.x * 8 + 7] = sm; }
   const int64_t row0 = (int64_t)blockIdx.x * TC_M;
   const int n0 = blockIdx.y * p.nt;
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + 8), accum_bar = smem_u32(bars + 16);
@@ -201,7 +203,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = s_misc[0];
-  const uint32_t kmask = s_misc[1];
+  const uint32_t kmask = (p.dbg_skip & 4) ? 0u : s_misc[1];
+  if (p.dbg_clock && tid == 64) p.dbg_clock[blockIdx.x * 8 + 1] = clock64();
   const int nb = p.nb0 + p.nb1;
   // stage sequence of this tile = (valid offsets in ascending k) x (channel blocks); split mode takes a chunk
   const int n_stage_all = __popc(kmask) * nb;
@@ -353,6 +356,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
         }
       }
     }
+    if (p.dbg_clock && tid == 64) p.dbg_clock[blockIdx.x * 8 + 2] = clock64();     // A producers done issuing
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int m = q * 32 + lane;
     const int64_t o = row0 + m;
@@ -360,7 +364,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
       mbar_wait(accum_bar, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
-    const bool live = o < p.n_out;
+    if (p.dbg_clock && tid == 64) p.dbg_clock[blockIdx.x * 8 + 3] = clock64();     // accumulator ready
+    const bool live = (o < p.n_out) && !(p.dbg_skip & 8);
     const int64_t orow = (live && p.out_row_map) ? (int64_t)__ldg(p.out_row_map + o) : o;
     for (int cbo = 0; cbo < p.nt / 32; ++cbo) {
       float y[32];
@@ -421,8 +426,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
     }
   }
 
+  if (p.dbg_clock && tid == 64) p.dbg_clock[blockIdx.x * 8 + 4] = clock64();       // epilogue stores issued
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (p.dbg_clock && tid == 64) p.dbg_clock[blockIdx.x * 8 + 5] = clock64();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols));
   }
@@ -529,7 +536,8 @@ static int g_tc_smem_budget = 112 * 1024;   // per CTA -> two CTAs per SM
 static int g_tc_dbg_skip = 0;
 static int g_tc_force_split = 0;            // 0 = heuristic, >0 = forced nsplit (1 disables)
 static int g_tc_target_ctas = 296;
-static int g_tc_pf_dist = 296;
+static int g_tc_pf_dist = 0;
+static long long *g_tc_dbg_clock = nullptr;
 
 }  // namespace osb
 
@@ -545,6 +553,7 @@ void osb_debug_set_tc(int use_gather4, int smem_budget) {
   if (smem_budget > 0) g_tc_smem_budget = smem_budget;
 }
 void osb_debug_set_tc3(int pf_dist) { g_tc_pf_dist = pf_dist; }
+void osb_debug_set_clock(void *buf) { g_tc_dbg_clock = (long long *)buf; }
 void osb_debug_set_tc2(int dbg_skip, int force_split, int target_ctas) {
   if (dbg_skip >= 0) g_tc_dbg_skip = dbg_skip;
   if (force_split >= 0) g_tc_force_split = force_split;
@@ -616,6 +625,7 @@ int osb_conv_fwd_tc(const void *src0, int32_t c0, int64_t n_src0, const void *sr
   p.out_split = (uint8_t *)out_split; p.out_f32 = out_f32; p.out_row_map = out_row_map;
   p.use_gather4 = g_tc_use_gather4;
   p.dbg_skip = g_tc_dbg_skip;
+  p.dbg_clock = g_tc_dbg_clock;
   p.src0_ptr = (const uint8_t *)src0; p.src1_ptr = (const uint8_t *)src1;
   p.pf_dist = (n_src0 == n_out && (c1 == 0 || n_src1 == n_out) && (K & 1)) ? g_tc_pf_dist : 0;
   const size_t need = osb_conv_tc_workspace_bytes(n_out, K, cin, cout);

@@ -81,3 +81,10 @@ def debug_set_tc(use_gather4=-1, smem_budget=0, dbg_skip=-1, force_split=-1, tar
         fn3 = C.lib().osb_debug_set_tc3
         fn3.restype, fn3.argtypes = None, [ctypes.c_int]
         fn3(pf_dist)
+
+
+def debug_set_clock(buf):
+    """tuning: int64 CUDA tensor [n_tiles, 8] receiving per-CTA clock64 stamps (None disables)."""
+    fn = C.lib().osb_debug_set_clock
+    fn.restype, fn.argtypes = None, [ctypes.c_void_p]
+    fn(C.ptr(buf))
