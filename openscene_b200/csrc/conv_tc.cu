@@ -365,8 +365,32 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
     if (p.dbg_clock && tid == 64) p.dbg_clock[blockIdx.x * 8 + 3] = clock64();     // accumulator ready
-    const bool live = (o < p.n_out) && !(p.dbg_skip & 8);
-    const int64_t orow = (live && p.out_row_map) ? (int64_t)__ldg(p.out_row_map + o) : o;
+    // Rows of this warp: tile rows [32q, 32q+32).  Global traffic goes through a 4 KB shared-memory staging
+    // tile per warp (pipeline stage 0 is idle by now) in the 128B-swizzled layout, so that every global
+    // load / store instruction moves 4 full 128-byte lines (lane -> row 4i + lane/8, 16-byte chunk lane%8)
+    // instead of 32 half-sectors.
+    const bool no_store = (p.dbg_skip & 8) != 0;
+    const uint32_t stg = smem_u32(smem) + q * 4096;
+    const int64_t wrow0 = row0 + q * 32;                         // first global row of this warp
+    const int rsub = lane >> 3, chunk = lane & 7;
+    int32_t my_orow = (int32_t)min(o, p.n_out - 1);
+    if (p.out_row_map && o < p.n_out) my_orow = __ldg(p.out_row_map + o);
+    auto lds128 = [](uint32_t a) { uint4 v; asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; };
+    auto sts128 = [](uint32_t a, uint4 v) { asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); };
+    const uint32_t my_line = stg + lane * 128;
+    const int sw = lane & 7;
+    // staged tile -> global: dst_row(r) gives the destination row index of tile row r (or -1)
+    auto flush_tile = [&](uint8_t *base, int64_t row_bytes, int64_t col_byte, bool mapped) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = 4 * i + rsub;
+        const uint4 v = lds128(stg + r * 128 + ((chunk ^ (r & 7)) << 4));
+        const int32_t mo = __shfl_sync(0xffffffffu, my_orow, r);
+        const int64_t grow = mapped ? (int64_t)mo : wrow0 + r;
+        if (wrow0 + r < p.n_out && !no_store)
+          *reinterpret_cast<uint4 *>(base + grow * row_bytes + col_byte + chunk * 16) = v;
+      }
+    };
     for (int cbo = 0; cbo < p.nt / 32; ++cbo) {
       float y[32];
       if (have_work) {
@@ -382,46 +406,65 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
         for (int j = 0; j < 32; ++j) y[j] = 0.f;
       }
       const int c0 = n0 + cbo * 32;              // first output channel of this 32-block
-      if (!live) continue;
       if (p.nsplit > 1) {                        // raw partial sums; k_conv_finish reduces + applies the epilogue
-        float4 *pp = reinterpret_cast<float4 *>(p.partial + ((int64_t)blockIdx.z * p.n_out + o) * p.cout_pad + c0);
 #pragma unroll
-        for (int g = 0; g < 8; ++g) pp[g] = make_float4(y[4 * g], y[4 * g + 1], y[4 * g + 2], y[4 * g + 3]);
+        for (int g = 0; g < 8; ++g)
+          sts128(my_line + ((g ^ sw) << 4), make_uint4(__float_as_uint(y[4 * g]), __float_as_uint(y[4 * g + 1]),
+                                                       __float_as_uint(y[4 * g + 2]), __float_as_uint(y[4 * g + 3])));
+        __syncwarp();
+        flush_tile(reinterpret_cast<uint8_t *>(p.partial + (int64_t)blockIdx.z * p.n_out * p.cout_pad), (int64_t)p.cout_pad * 4,
+                   (int64_t)c0 * 4, false);
+        __syncwarp();
         continue;
       }
-      if (c0 >= p.cout) continue;
+      if (c0 >= p.cout) continue;               // warp-uniform
 #pragma unroll
       for (int j = 0; j < 32; ++j) y[j] = fmaf(y[j], s_scale[cbo * 32 + j], s_shift[cbo * 32 + j]);
-      if (p.res) {
-        const uint4 *rp = reinterpret_cast<const uint4 *>(p.res + o * (int64_t)p.cout * 4 + (c0 >> 5) * 128);
+      if (p.res) {                               // residual tile: coalesced load -> smem -> own row
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = 4 * i + rsub;
+          uint4 v = make_uint4(0, 0, 0, 0);
+          if (wrow0 + r < p.n_out)
+            v = __ldg(reinterpret_cast<const uint4 *>(p.res + (wrow0 + r) * (int64_t)p.cout * 4 + (c0 >> 5) * 128 + chunk * 16));
+          sts128(stg + r * 128 + ((chunk ^ (r & 7)) << 4), v);
+        }
+        __syncwarp();
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          const uint4 hq = __ldg(rp + g), lq = __ldg(rp + 4 + g);
+          const uint4 hq = lds128(my_line + ((g ^ sw) << 4)), lq = lds128(my_line + (((4 + g) ^ sw) << 4));
           const __nv_bfloat16 *hh = reinterpret_cast<const __nv_bfloat16 *>(&hq);
           const __nv_bfloat16 *ll = reinterpret_cast<const __nv_bfloat16 *>(&lq);
 #pragma unroll
           for (int j = 0; j < 8; ++j) y[g * 8 + j] += join_bf16(hh[j], ll[j]);
         }
+        __syncwarp();
       }
       if (p.relu) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
       }
       if (p.out_split) {
-        uint4 *op = reinterpret_cast<uint4 *>(p.out_split + o * (int64_t)p.cout * 4 + (c0 >> 5) * 128);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           __align__(16) __nv_bfloat16 hh[8], ll[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) split_bf16(y[g * 8 + j], hh[j], ll[j]);
-          op[g] = *reinterpret_cast<const uint4 *>(hh);
-          op[4 + g] = *reinterpret_cast<const uint4 *>(ll);
+          sts128(my_line + ((g ^ sw) << 4), *reinterpret_cast<const uint4 *>(hh));
+          sts128(my_line + (((4 + g) ^ sw) << 4), *reinterpret_cast<const uint4 *>(ll));
         }
+        __syncwarp();
+        flush_tile(p.out_split, (int64_t)p.cout * 4, (int64_t)(c0 >> 5) * 128, false);
+        __syncwarp();
       }
       if (p.out_f32) {
-        float4 *op = reinterpret_cast<float4 *>(p.out_f32 + orow * (int64_t)p.cout + c0);
 #pragma unroll
-        for (int g = 0; g < 8; ++g) op[g] = make_float4(y[4 * g], y[4 * g + 1], y[4 * g + 2], y[4 * g + 3]);
+        for (int g = 0; g < 8; ++g)
+          sts128(my_line + ((g ^ sw) << 4), make_uint4(__float_as_uint(y[4 * g]), __float_as_uint(y[4 * g + 1]),
+                                                       __float_as_uint(y[4 * g + 2]), __float_as_uint(y[4 * g + 3])));
+        __syncwarp();
+        flush_tile(reinterpret_cast<uint8_t *>(p.out_f32), (int64_t)p.cout * 4, (int64_t)c0 * 4, p.out_row_map != nullptr);
+        __syncwarp();
       }
     }
   }
