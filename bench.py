@@ -30,7 +30,7 @@ import torch  # noqa: E402
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='osb200', choices=['osb200', 'reference'])
     ap.add_argument('--workload', default='config2_200k')
@@ -57,7 +57,7 @@ class ClockSampler:
     def __init__(self, index):
         self.rows, self.proc = [], None
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '200',
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '50',
                                           '-i', str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -228,13 +228,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local) if rank == 0 else None     # started before warm-up: nvidia-smi start-up stalls the GPU briefly
+    sampler = ClockSampler(local) if rank == 0 else None     # nvidia-smi start-up stalls the GPU briefly: start it early
+    if sampler:
+        time.sleep(1.5)
+        sampler.rows.clear()                                   # samples from here on are under load (warm-up + timed steps)
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
-    if sampler:
-        time.sleep(1.5)
-        sampler.rows.clear()
     l0 = _cabi.lib().osb_launch_count()
     ms_dev = timed(step_device, args.steps)
     launches = _cabi.lib().osb_launch_count() - l0

@@ -60,3 +60,17 @@ def test_train_mode_batchnorm_and_backward_match_oracle():
     assert worst < 5e-2
     # running statistics were updated identically
     assert torch.allclose(m64.bn0.bn.running_mean.float(), mg.bn0.bn.running_mean.cpu(), atol=1e-5)
+
+
+def test_distill_step_reduces_loss():
+    """run/distill.py:311-334 on the drop-in surface: a few Adam steps on one scene lower the cosine loss."""
+    from openscene_b200 import distill
+    c = torch.from_numpy(synth.random_cloud(1200, 18, seed=9))
+    f = torch.ones(len(c), 3)
+    g = torch.Generator().manual_seed(3)
+    mask = torch.rand(len(c), generator=g) < 0.6
+    tgt = torch.randn(int(mask.sum()), 64, generator=g).half()
+    model = synth.build_model('MinkUNet14A', 64, seed=1).to(DEV).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    losses = [float(distill.distill_step(model, opt, c, f, tgt, mask)) for _ in range(6)]
+    assert losses[-1] < losses[0] - 0.02, losses
