@@ -50,47 +50,51 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi sampling during the timed region (B200_PROFILING.md 'clocks' line)."""
-    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    """SM clock / throttle-reason sampling during the timed region (B200_PROFILING.md 'clocks' line).
+    NVML is polled in-process every 25 ms; spawning `nvidia-smi -lms` instead stalls the GPU for milliseconds per
+    query and inflated ms_per_step by ~45% when it ran during the timed region."""
+    REASONS = {'hw_slowdown': 0x8, 'sw_thermal_slowdown': 0x20, 'hw_thermal_slowdown': 0x40, 'sw_power_cap': 0x4}
 
     def __init__(self, index):
-        self.rows, self.proc = [], None
+        self.sm, self.mx, self.reasons, self.power = [], None, set(), []
+        self._stop = threading.Event()
+        self.ok = False
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '50',
-                                          '-i', str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+            self.t = threading.Thread(target=self._run, daemon=True)
             self.t.start()
-        except Exception:
-            self.proc = None
+        except Exception as e:            # noqa: BLE001
+            self.err = str(e)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for name, bit in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1e3)
+            except Exception:             # noqa: BLE001
+                pass
+            self._stop.wait(0.025)
+
+    def reset(self):
+        self.sm.clear(); self.reasons.clear(); self.power.clear()
 
     def stop(self):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in self.rows:
-            f = [x.strip() for x in r.split(',')]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith('active'):
-                    reasons.add(n)
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+        if not self.ok:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvml unavailable: ' + getattr(self, 'err', '')]}
+        self._stop.set()
+        self.t.join(timeout=1)
+        return {'sm_mhz': float(np.median(self.sm)) if self.sm else None, 'sm_max_mhz': self.mx,
+                'reasons': sorted(self.reasons), 'samples': len(self.sm),
+                'power_w_max': max(self.power) if self.power else None}
 
 
 def algorithmic_bytes(census):
@@ -228,13 +232,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local) if rank == 0 else None     # nvidia-smi start-up stalls the GPU briefly: start it early
-    if sampler:
-        time.sleep(1.5)
-        sampler.rows.clear()                                   # samples from here on are under load (warm-up + timed steps)
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
+    if sampler:
+        sampler.reset()                                        # keep only samples taken during the timed steps
     l0 = _cabi.lib().osb_launch_count()
     ms_dev = timed(step_device, args.steps)
     launches = _cabi.lib().osb_launch_count() - l0

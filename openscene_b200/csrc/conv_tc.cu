@@ -22,10 +22,7 @@
 //   1           TMA tile::gather4 (4 rows x 128 B per instruction): the TMA unit spends ~20-25 cycles per
 //               gather4 instruction regardless of bytes (~23 B/clk/SM), which bounds the whole kernel;
 //   0           one TMA row load per row (cross-check path).
-#include "common.cuh"
-
-#include <cuda.h>
-#include <cudaTypedefs.h>
+#include "tc_ptx.cuh"
 #include <algorithm>
 
 namespace osb {
@@ -55,78 +52,6 @@ struct ConvTcParams {
   int dbg_skip;          // tuning only: bit0 = no A gathers, bit1 = no B loads, bit2 = no main loop, bit3 = no stores
   long long *dbg_clock;  // tuning only: per-CTA timestamps [gridDim.x][8] (may be NULL)
 };
-
-// ------------------------------------------------------------------------------------ PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  for (uint32_t it = 0; !done; ++it) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (it > (1u << 26)) __trap();   // a lost TMA / MMA completion must not hang the GPU
-  }
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-// this thread's arrival on `bar` fires when all of its prior cp.async have landed (count pre-armed at init)
-__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int col, int r0, int r1,
-                                            int r2, int r3) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(tm), "r"(bar), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-}
-// K-major, 128-byte swizzle: 8-row groups 1024 B apart, descriptor version 1 (sm_100)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
 
 // ------------------------------------------------------------------------------------ the kernel
 __global__ void __launch_bounds__(TC_THREADS)
@@ -558,27 +483,30 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   return fn;
 }
 
-// 2-D bf16 tensor [rows, cols_elems] with row pitch cols_elems*2 bytes; box {64 elems, box_rows}; 128B swizzle
-static int make_tmap(CUtensorMap *tm, const void *base, uint64_t cols_elems, uint64_t rows, uint32_t box_rows) {
+// 2-D tensor [rows, cols_elems] of 2-byte elements with row pitch cols_elems*2 bytes; box {64 elems, box_rows}; 128B swizzle
+int make_tmap_2b(CUtensorMap *tm, const void *base, uint64_t cols_elems, uint64_t rows, uint32_t box_rows, int is_f16) {
   auto enc = get_encode();
   OSB_CHECK(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t gdim[2] = {cols_elems, rows};
   cuuint64_t gstride[1] = {cols_elems * 2};
   cuuint32_t box[2] = {64, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(tm, is_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base),
+                   gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   OSB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) base=%p cols=%llu rows=%llu box_rows=%u", (int)r, base,
             (unsigned long long)cols_elems, (unsigned long long)rows, box_rows);
   return 0;
+}
+static int make_tmap(CUtensorMap *tm, const void *base, uint64_t cols_elems, uint64_t rows, uint32_t box_rows) {
+  return make_tmap_2b(tm, base, cols_elems, rows, box_rows, 0);
 }
 
 static int g_tc_use_gather4 = 2;            // A operand path: 2 = cp.async (default), 1 = TMA gather4, 0 = TMA row loads
 static int g_tc_smem_budget = 112 * 1024;   // per CTA -> two CTAs per SM
 static int g_tc_dbg_skip = 0;
 static int g_tc_force_split = 0;            // 0 = heuristic, >0 = forced nsplit (1 disables)
-static int g_tc_target_ctas = 296;
+static int g_tc_target_ctas = 148;          // split small launches until ~one CTA per SM (sweep: profiles/r01_tune_conv.md)
 static int g_tc_pf_dist = 0;
 static long long *g_tc_dbg_clock = nullptr;
 

@@ -29,9 +29,10 @@ __device__ __forceinline__ int floordiv(int a, int s) { return a >= 0 ? a / s : 
 // ------------------------------------------------------------------------------------ kernels
 __global__ void k_morton_from_coords(const int4 *__restrict__ coords, int64_t n, int32_t new_ts,
                                      uint64_t *__restrict__ morton, int32_t *__restrict__ idx,
-                                     int32_t *__restrict__ status) {
+                                     int32_t *__restrict__ status, unsigned long long *__restrict__ bits) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  unsigned long long k_or = 0ull, k_and = ~0ull;
+  if (i < n) {
   int4 c = coords[i];  // (b, x, y, z)
   bool bad = c.x < 0 || c.x >= 1024 || abs(c.y) >= kCoordLimit || abs(c.z) >= kCoordLimit || abs(c.w) >= kCoordLimit;
   if (bad) { atomicOr(status, 1); c = make_int4(0, 0, 0, 0); }
@@ -40,8 +41,18 @@ __global__ void k_morton_from_coords(const int4 *__restrict__ coords, int64_t n,
     c.z = floordiv(c.z, new_ts) * new_ts;
     c.w = floordiv(c.w, new_ts) * new_ts;
   }
-  morton[i] = morton_key(c.x, c.y, c.z, c.w);
+  const uint64_t key = morton_key(c.x, c.y, c.z, c.w);
+  morton[i] = key;
   idx[i] = (int32_t)i;
+  k_or = key; k_and = key;
+  }
+  // bits that differ between keys = OR & ~AND: the radix sort only needs those digit positions
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    k_or |= __shfl_xor_sync(0xffffffffu, k_or, o);
+    k_and &= __shfl_xor_sync(0xffffffffu, k_and, o);
+  }
+  if ((threadIdx.x & 31) == 0) { atomicOr(bits, k_or); atomicAnd(bits + 1, k_and); }
 }
 
 // level 0: permute coordinates into Morton order, build inverse permutation, flag duplicates
@@ -162,6 +173,16 @@ static size_t cub_sort_bytes(int64_t n) {
                                   (int32_t *)nullptr, (int)n, 0, 64, (cudaStream_t)0);
   return b;
 }
+// digit range [lo, hi) of the bits in which the keys differ (OR & ~AND), rounded to the 8-bit radix passes
+static void varying_bits(unsigned long long k_or, unsigned long long k_and, int *lo, int *hi) {
+  const unsigned long long diff = k_or & ~k_and;
+  if (diff == 0) { *lo = 0; *hi = 8; return; }
+  int l = 0, h = 64;
+  while (!((diff >> l) & 1ull)) ++l;
+  while (!((diff >> (h - 1)) & 1ull)) --h;
+  *lo = l; *hi = h;
+}
+
 static size_t cub_scan_bytes(int64_t n) {
   size_t b = 0;
   cub::DeviceScan::InclusiveSum(nullptr, b, (const int32_t *)nullptr, (int32_t *)nullptr, (int)n, (cudaStream_t)0);
@@ -221,11 +242,19 @@ int osb_coordset_build(const int32_t *coords, int64_t n, int32_t *coords_int, in
   size_t sort_bytes = cub_sort_bytes(n);
   void *cub_tmp = cv.take<char>(sort_bytes);
   OSB_CHECK(cv.ok, "osb_coordset_build: workspace too small (%zu bytes)", ws_bytes);
+  const unsigned long long bits_init[2] = {0ull, ~0ull};
+  unsigned long long *bits = reinterpret_cast<unsigned long long *>(status + 8);
   OSB_CUDA(cudaMemsetAsync(status, 0, 8, stream));
+  OSB_CUDA(cudaMemcpyAsync(bits, bits_init, 16, cudaMemcpyHostToDevice, stream));
   const unsigned nb = (unsigned)ceil_div(n, 256);
-  k_morton_from_coords<<<nb, 256, 0, stream>>>((const int4 *)coords, n, 1, morton, idx, status);
+  k_morton_from_coords<<<nb, 256, 0, stream>>>((const int4 *)coords, n, 1, morton, idx, status, bits);
   OSB_LAUNCH_CHECK();
-  OSB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, sort_bytes, morton, morton_s, idx, perm, (int)n, 0, 64, stream));
+  unsigned long long hb[2];
+  OSB_CUDA(cudaMemcpyAsync(hb, bits, 16, cudaMemcpyDeviceToHost, stream));
+  OSB_CUDA(cudaStreamSynchronize(stream));
+  int lo, hi;
+  varying_bits(hb[0], hb[1], &lo, &hi);
+  OSB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, sort_bytes, morton, morton_s, idx, perm, (int)n, lo, hi, stream));
   k_permute_coords<<<nb, 256, 0, stream>>>((const int4 *)coords, perm, morton_s, n, (int4 *)coords_int, inv_perm, status);
   OSB_LAUNCH_CHECK();
   if (osb_hash_build(coords_int, n, slots, cap, stream_)) return 1;
@@ -249,11 +278,19 @@ int osb_coordset_stride(const int32_t *coords_fine, int64_t n, int32_t new_ts, i
   size_t sort_bytes = cub_sort_bytes(n), scan_bytes = cub_scan_bytes(n);
   void *cub_tmp = cv.take<char>(sort_bytes > scan_bytes ? sort_bytes : scan_bytes);
   OSB_CHECK(cv.ok, "osb_coordset_stride: workspace too small (%zu bytes)", ws_bytes);
+  const unsigned long long bits_init[2] = {0ull, ~0ull};
+  unsigned long long *bits = reinterpret_cast<unsigned long long *>(status + 8);
   OSB_CUDA(cudaMemsetAsync(status, 0, 8, stream));
+  OSB_CUDA(cudaMemcpyAsync(bits, bits_init, 16, cudaMemcpyHostToDevice, stream));
   const unsigned nb = (unsigned)ceil_div(n, 256);
-  k_morton_from_coords<<<nb, 256, 0, stream>>>((const int4 *)coords_fine, n, new_ts, key, idx, status);
+  k_morton_from_coords<<<nb, 256, 0, stream>>>((const int4 *)coords_fine, n, new_ts, key, idx, status, bits);
   OSB_LAUNCH_CHECK();
-  OSB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, sort_bytes, key, key_s, idx, order, (int)n, 0, 64, stream));
+  unsigned long long hb[2];
+  OSB_CUDA(cudaMemcpyAsync(hb, bits, 16, cudaMemcpyDeviceToHost, stream));
+  OSB_CUDA(cudaStreamSynchronize(stream));
+  int lo, hi;
+  varying_bits(hb[0], hb[1], &lo, &hi);
+  OSB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, sort_bytes, key, key_s, idx, order, (int)n, lo, hi, stream));
   k_run_heads<<<nb, 256, 0, stream>>>(key_s, n, heads);
   OSB_LAUNCH_CHECK();
   OSB_CUDA(cub::DeviceScan::InclusiveSum(cub_tmp, scan_bytes, heads, ids, (int)n, stream));

@@ -6,6 +6,7 @@
 // point, the text matrix (K*C*2 bytes, <= 245 KB) stays in L1/L2.
 #include "common.cuh"
 #include <algorithm>
+#include <stdlib.h>
 
 namespace osb {
 
@@ -129,6 +130,17 @@ k_match_ensemble(const float *__restrict__ feat3d, const __half *__restrict__ fe
   }
 }
 
+// tensor-core implementation (match_tc.cu)
+int match_tc_run(const void *feat, int feat_is_f16, const void *feat2_f16, const float *sel_a, const float *sel_b, int c,
+                 const int64_t *inds_reverse, int64_t n_pts, const void *text_f16, int k_text, int normalize,
+                 void *scores_f16, int64_t *label, float *smax, void *feat_out_f16, cudaStream_t stream);
+
+static bool use_simt() {   // OSB_MATCH_SIMT=1 selects the CUDA-core kernels below (cross-check path)
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("OSB_MATCH_SIMT"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
 static unsigned match_grid(int64_t n_pts) {
   return (unsigned)std::min<int64_t>(ceil_div(n_pts, 8), 148 * 8);
 }
@@ -146,6 +158,9 @@ int osb_match_scores(const void *feat, int32_t feat_is_f16, int64_t n_vox, int32
   OSB_CHECK(c == 512 || c == 768, "osb_match_scores: feature width %d unsupported (OpenScene uses 512 / 768)", c);
   OSB_CHECK(k_text >= 1 && n_vox > 0, "osb_match_scores: bad shape");
   if (n_pts == 0) return 0;
+  if (!use_simt())
+    return match_tc_run(feat, feat_is_f16, nullptr, nullptr, nullptr, c, inds_reverse, n_pts, text_f16, k_text, normalize,
+                        scores_f16, label, smax, nullptr, stream);
   const unsigned grid = match_grid(n_pts);
   const __half2 *text = (const __half2 *)text_f16;
   __half *scores = (__half *)scores_f16;
@@ -170,6 +185,9 @@ int osb_match_ensemble(const float *feat3d, const void *feat2d_f16, int64_t n_vo
   OSB_CHECK(c == 512 || c == 768, "osb_match_ensemble: feature width %d unsupported", c);
   OSB_CHECK(k_text >= 1 && n_vox > 0, "osb_match_ensemble: bad shape");
   if (n_pts == 0) return 0;
+  if (!use_simt())
+    return match_tc_run(feat3d, 0, feat2d_f16, smax3d, smax2d, c, inds_reverse, n_pts, text_f16, k_text, 0, scores_f16, label,
+                        nullptr, feat_out_f16, stream);
   const unsigned grid = match_grid(n_pts);
   if (c == 768)
     k_match_ensemble<12><<<grid, 256, 0, stream>>>(feat3d, (const __half *)feat2d_f16, inds_reverse, n_pts, smax3d, smax2d,
