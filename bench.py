@@ -50,14 +50,14 @@ def peaks():
 
 
 class ClockSampler:
-    """SM clock / throttle-reason sampling during the timed region (B200_PROFILING.md 'clocks' line).
-    NVML is polled in-process every 25 ms; spawning `nvidia-smi -lms` instead stalls the GPU for milliseconds per
-    query and inflated ms_per_step by ~45% when it ran during the timed region."""
+    """SM clock / throttle-reason samples taken DURING the timed region (B200_PROFILING.md 'clocks' line) through NVML,
+    from the benchmark thread itself right after a step has been enqueued (the GPU is still executing it) and outside
+    the CUDA-event pair of any step.  A background poller (nvidia-smi -lms, or an NVML thread) contends with kernel
+    submission and inflated ms_per_step by 45-100% when tried."""
     REASONS = {'hw_slowdown': 0x8, 'sw_thermal_slowdown': 0x20, 'hw_thermal_slowdown': 0x40, 'sw_power_cap': 0x4}
 
     def __init__(self, index):
         self.sm, self.mx, self.reasons, self.power = [], None, set(), []
-        self._stop = threading.Event()
         self.ok = False
         try:
             import pynvml
@@ -65,33 +65,26 @@ class ClockSampler:
             self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(index)
             self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
             self.ok = True
-            self.t = threading.Thread(target=self._run, daemon=True)
-            self.t.start()
         except Exception as e:            # noqa: BLE001
             self.err = str(e)
 
-    def _run(self):
+    def sample(self):
+        if not self.ok:
+            return
         nv = self.nv
-        while not self._stop.is_set():
-            try:
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
-                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                for name, bit in self.REASONS.items():
-                    if r & bit:
-                        self.reasons.add(name)
-                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1e3)
-            except Exception:             # noqa: BLE001
-                pass
-            self._stop.wait(0.025)
-
-    def reset(self):
-        self.sm.clear(); self.reasons.clear(); self.power.clear()
+        try:
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            for name, bit in self.REASONS.items():
+                if r & bit:
+                    self.reasons.add(name)
+            self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1e3)
+        except Exception:                 # noqa: BLE001
+            pass
 
     def stop(self):
         if not self.ok:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvml unavailable: ' + getattr(self, 'err', '')]}
-        self._stop.set()
-        self.t.join(timeout=1)
         return {'sm_mhz': float(np.median(self.sm)) if self.sm else None, 'sm_max_mhz': self.mx,
                 'reasons': sorted(self.reasons), 'samples': len(self.sm),
                 'power_w_max': max(self.power) if self.power else None}
@@ -217,13 +210,15 @@ def main():
         _, label, _ = matching._scores(out, None, text, normalize=True)
         return label.cpu()
 
-    def timed(fn, k):
+    def timed(fn, k, sampler=None):
         evs = []
-        for _ in range(k):
+        for i in range(k):
             flush.zero_()                                            # L2 flush, outside the timed events
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); fn(); b.record()
             evs.append((a, b))
+            if sampler is not None and i % 4 == 1:
+                sampler.sample()                                     # GPU still busy with this step; outside its event pair
         torch.cuda.synchronize()
         return sum(a.elapsed_time(b) for a, b in evs)
 
@@ -236,10 +231,8 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
-    if sampler:
-        sampler.reset()                                        # keep only samples taken during the timed steps
     l0 = _cabi.lib().osb_launch_count()
-    ms_dev = timed(step_device, args.steps)
+    ms_dev = timed(step_device, args.steps, sampler)
     launches = _cabi.lib().osb_launch_count() - l0
     barrier()
     clocks = sampler.stop() if sampler else None

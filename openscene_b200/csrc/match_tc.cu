@@ -76,60 +76,74 @@ k_match_tc(const __grid_constant__ CUtensorMap tmT, const MatchTcParams p) {
 
   if (warp < 8) {
     // ============================ A producers: 16 rows per warp =============================
-    for (int rr = 0; rr < 16; ++rr) {
-      const int r = warp * 16 + rr;
-      const int64_t pt = row0 + r;
-      float v[2 * NP];
-      if (pt < p.n_pts) {
-        const int64_t vox = p.inds_reverse ? __ldg(p.inds_reverse + pt) : pt;
-        bool second = false;
-        if (p.feat2 != nullptr) second = (p.sel_a == nullptr) ? true : (__ldg(p.sel_a + pt) < __ldg(p.sel_b + pt));
-        const bool f16 = second || p.feat_is_f16;
-        const void *src = second ? (const void *)p.feat2 : p.feat;
-        float ss = 0.f;
-        if (f16) {
-          const __half2 *q = reinterpret_cast<const __half2 *>(src) + vox * (C / 2);
+    // RB rows are in flight per warp (loads of all RB rows are issued before any is consumed): 8 warps x RB x 3 KB
+    // of outstanding loads per SM is what it takes to keep HBM busy from one CTA per SM.
+    constexpr int RB = 4;
+    for (int rr0 = 0; rr0 < 16; rr0 += RB) {
+      float v[RB][2 * NP];
+      bool f16[RB], live[RB];
+      float ss[RB];
 #pragma unroll
-          for (int j = 0; j < NP; ++j) {
-            const float2 f = __half22float2(__ldg(q + lane + 32 * j));
-            v[2 * j] = f.x; v[2 * j + 1] = f.y;
-            ss += f.x * f.x + f.y * f.y;
+      for (int u = 0; u < RB; ++u) {
+        const int64_t pt = row0 + warp * 16 + rr0 + u;
+        live[u] = pt < p.n_pts;
+        f16[u] = false;
+        ss[u] = 0.f;
+        if (live[u]) {
+          const int64_t vox = p.inds_reverse ? __ldg(p.inds_reverse + pt) : pt;
+          bool second = false;
+          if (p.feat2 != nullptr) second = (p.sel_a == nullptr) ? true : (__ldg(p.sel_a + pt) < __ldg(p.sel_b + pt));
+          f16[u] = second || p.feat_is_f16;
+          const void *src = second ? (const void *)p.feat2 : p.feat;
+          if (f16[u]) {
+            const __half2 *q = reinterpret_cast<const __half2 *>(src) + vox * (C / 2);
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+              const float2 f = __half22float2(__ldg(q + lane + 32 * j));
+              v[u][2 * j] = f.x; v[u][2 * j + 1] = f.y;
+            }
+          } else {
+            const float2 *q = reinterpret_cast<const float2 *>(src) + vox * (C / 2);
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+              const float2 f = __ldg(q + lane + 32 * j);
+              v[u][2 * j] = f.x; v[u][2 * j + 1] = f.y;
+            }
           }
         } else {
-          const float2 *q = reinterpret_cast<const float2 *>(src) + vox * (C / 2);
 #pragma unroll
-          for (int j = 0; j < NP; ++j) {
-            const float2 f = __ldg(q + lane + 32 * j);
-            v[2 * j] = f.x; v[2 * j + 1] = f.y;
-            ss += f.x * f.x + f.y * f.y;
-          }
+          for (int j = 0; j < 2 * NP; ++j) v[u][j] = 0.f;
         }
+      }
+#pragma unroll
+      for (int u = 0; u < RB; ++u) {
+        const int r = warp * 16 + rr0 + u;
+        const int64_t pt = row0 + r;
         if (p.normalize) {
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-          float nrm = sqrtf(ss);
+          for (int j = 0; j < 2 * NP; ++j) ss[u] = fmaf(v[u][j], v[u][j], ss[u]);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) ss[u] += __shfl_xor_sync(0xffffffffu, ss[u], o);
+          float nrm = sqrtf(ss[u]);
           float d;
-          if (f16) {   // the reference takes norm, +1e-5 and the division on an fp16 tensor (evaluate.py:303-305)
+          if (f16[u]) {   // the reference takes norm, +1e-5 and the division on an fp16 tensor (evaluate.py:303-305)
             nrm = __half2float(__float2half_rn(nrm));
             d = __half2float(__float2half_rn(nrm + 1e-5f));
           } else {
             d = nrm + 1e-5f;
           }
 #pragma unroll
-          for (int j = 0; j < 2 * NP; ++j) v[j] = v[j] / d;
+          for (int j = 0; j < 2 * NP; ++j) v[u][j] = v[u][j] / d;
         }
-      } else {
+        // chunk j of this row: lane holds elements 2*lane, 2*lane+1 -> bytes [4*lane, 4*lane+4) of the 128-byte line
+        const uint32_t line = smem_u32(sA) + r * 128 + ((((4 * lane) >> 4) ^ (r & 7)) << 4) + ((4 * lane) & 15);
 #pragma unroll
-        for (int j = 0; j < 2 * NP; ++j) v[j] = 0.f;
-      }
-      // chunk j of this row: lane holds elements 2*lane, 2*lane+1 -> bytes [4*lane, 4*lane+4) of the 128-byte line
-      const uint32_t line = smem_u32(sA) + r * 128 + ((((4 * lane) >> 4) ^ (r & 7)) << 4) + ((4 * lane) & 15);
-#pragma unroll
-      for (int j = 0; j < NP; ++j) {
-        const __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);       // the reference's `.half()`
-        asm volatile("st.shared.b32 [%0], %1;" ::"r"(line + j * (MT_M * 128)), "r"(*reinterpret_cast<const uint32_t *>(&h)) : "memory");
-        if (p.feat_out != nullptr && pt < p.n_pts)
-          reinterpret_cast<__half2 *>(p.feat_out)[pt * (C / 2) + lane + 32 * j] = h;
+        for (int j = 0; j < NP; ++j) {
+          const __half2 h = __floats2half2_rn(v[u][2 * j], v[u][2 * j + 1]);       // the reference's `.half()`
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(line + j * (MT_M * 128)), "r"(*reinterpret_cast<const uint32_t *>(&h)) : "memory");
+          if (p.feat_out != nullptr && live[u])
+            reinterpret_cast<__half2 *>(p.feat_out)[pt * (C / 2) + lane + 32 * j] = h;
+        }
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");           // generic-proxy writes -> UMMA reads
