@@ -284,7 +284,7 @@ class _ConvBase(nn.Module):
     def _w3(self):
         return self.kernel.unsqueeze(0) if self.kernel.dim() == 2 else self.kernel
 
-    def _apply(self, input, kmap, n_out):
+    def _run_conv(self, input, kmap, n_out):
         """Inference (grad disabled) with channel counts that are multiples of 32 runs on the tcgen05 kernel
         (bf16x3 split operands, ~1e-5 relative); everything else on the exact-fp32 kernels with autograd."""
         x = input._F
@@ -319,7 +319,7 @@ class MinkowskiConvolution(_ConvBase):
             ts_out = cm.stride(ts, self.stride) if self.stride > 1 else ts
             kmap = cm.kernel_map(ts, ts_out, self.kernel_size, self.dilation)
         n_out = cm.sets[ts_out].n
-        out = self._apply(input, kmap, n_out)
+        out = self._run_conv(input, kmap, n_out)
         if self.bias is not None:
             out = out + self.bias
         return SparseTensor._wrap(out, cm, ts_out)
@@ -339,7 +339,7 @@ class MinkowskiConvolutionTranspose(_ConvBase):
         else:
             kmap = cm.kernel_map(ts_out, ts, self.kernel_size, self.dilation).transposed()
         n_out = cm.sets[ts_out].n
-        out = self._apply(input, kmap, n_out)
+        out = self._run_conv(input, kmap, n_out)
         if self.bias is not None:
             out = out + self.bias
         return SparseTensor._wrap(out, cm, ts_out)
