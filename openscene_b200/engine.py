@@ -20,6 +20,10 @@ from . import tc
 from .coords import CoordinateManager
 
 
+def _al(x):
+    return (x + 255) & ~255
+
+
 def _fold_bn(bn_module):
     bn = bn_module.bn
     scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).float().contiguous()
@@ -29,7 +33,7 @@ def _fold_bn(bn_module):
 
 class _Conv:
     """Packed weights + folded BN of one convolution."""
-    __slots__ = ('K', 'cin', 'cout', 'wpack', 'w3', 'scale', 'shift', 'ks', 'stride', 'transpose')
+    __slots__ = ('K', 'cin', 'cout', 'wpack', 'w3', 'scale', 'shift', 'ks', 'stride', 'transpose', 'wpack_a', 'scale_a', 'shift_a')
 
     def __init__(self, conv, bn=None, keep_f32=False):
         w3 = conv.kernel.detach()
@@ -40,6 +44,10 @@ class _Conv:
         self.w3 = w3.float().contiguous() if keep_f32 else None
         self.wpack = tc.pack_weights(w3) if (self.cin % 32 == 0 and self.cout % 32 == 0) else None
         self.scale, self.shift = _fold_bn(bn) if bn is not None else (None, None)
+        # raw device addresses for the low-overhead launch path (tensors above keep the memory alive)
+        self.wpack_a = self.wpack.data_ptr() if self.wpack is not None else 0
+        self.scale_a = self.scale.data_ptr() if self.scale is not None else 0
+        self.shift_a = self.shift.data_ptr() if self.shift is not None else 0
 
 
 class FusedMinkUNet:
@@ -65,6 +73,7 @@ class FusedMinkUNet:
             self.final = _Conv(net.final, None, keep_f32=True)
         self.out_channels = self.final.cout
         self.last_cm = None
+        self._ws = None
 
     @staticmethod
     def _blocks(seq):
@@ -77,24 +86,47 @@ class FusedMinkUNet:
         return out
 
     # ---------------------------------------------------------------------------------------
-    @staticmethod
-    def _run(cv, srcs, nbr, n_out, res=None, relu=True, out_f32=False, row_map=None):
-        (s0, c0), (s1, c1) = srcs[0], (srcs[1] if len(srcs) > 1 else (None, 0))
-        assert c0 + c1 == cv.cin
-        o_split, o_f32 = tc.conv_tc(s0, c0, s1, c1, nbr, n_out, cv.K, cv.wpack, cv.cout, cv.scale, cv.shift, res, relu,
-                                    out_split=not out_f32, out_f32=out_f32, out_row_map=row_map)
-        return o_f32 if out_f32 else o_split
+    # Launch path: activations of one forward live in ONE arena tensor; layers are addressed by raw
+    # device pointers and every convolution is a single ctypes call with prebuilt integer arguments
+    # (no per-layer torch allocation, pointer boxing or workspace query: the Python dispatch cost per
+    # layer has to stay below the ~20 us the coarse-level kernels take).
+    def _plan_bytes(self, n):
+        """Upper bound of split-row bytes for all activations of one forward (256-byte aligned slices)."""
+        total = _al(n[0] * 4 * self.stem.cout)
+        for l, (dconv, blocks) in enumerate(self.enc):
+            total += _al(n[l + 1] * 4 * dconv.cout)
+            for (c1, c2, ds) in blocks:
+                total += _al(n[l + 1] * 4 * c1.cout) + _al(n[l + 1] * 4 * c2.cout) + (_al(n[l + 1] * 4 * ds.cout) if ds else 0)
+        for j, (uconv, blocks) in enumerate(self.dec):
+            l = 3 - j
+            total += _al(n[l] * 4 * uconv.cout)
+            for (c1, c2, ds) in blocks:
+                total += _al(n[l] * 4 * c1.cout) + _al(n[l] * 4 * c2.cout) + (_al(n[l] * 4 * ds.cout) if ds else 0)
+        return total
 
-    def _stage(self, blocks, srcs, nbr3, n):
+    def _conv(self, cv, srcs, nbr_a, n_out, res_a=0, relu=1, out_f32_a=0, row_map_a=0):
+        """srcs: [(addr, channels, rows)] (one or two).  Returns the address of the split output (or 0)."""
+        (s0, c0, r0) = srcs[0]
+        (s1, c1, r1) = srcs[1] if len(srcs) > 1 else (0, 0, 0)
+        out_a = 0
+        if not out_f32_a:
+            out_a = self._cursor
+            self._cursor += _al(n_out * 4 * cv.cout)
+        rc = self._fn(s0, c0, r0, s1, c1, r1, nbr_a, n_out, cv.K, cv.wpack_a, cv.cout, cv.scale_a, cv.shift_a, res_a, relu,
+                      out_a, out_f32_a, row_map_a, self._ws_a, self._ws_bytes, self._stream)
+        if rc:
+            C.check(rc, 'osb_conv_fwd_tc')
+        return out_a
+
+    def _stage(self, blocks, srcs, nbr3_a, n):
         x = srcs
         for (c1, c2, ds) in blocks:
-            y = self._run(c1, x, nbr3, n, relu=True)
+            y = self._conv(c1, x, nbr3_a, n)
             if ds is not None:
-                r = self._run(ds, x, None, n, relu=False)
+                r = self._conv(ds, x, 0, n, relu=0)
             else:
-                assert len(x) == 1
                 r = x[0][0]
-            x = [(self._run(c2, [(y, c1.cout)], nbr3, n, res=r, relu=True), c2.cout)]
+            x = [(self._conv(c2, [(y, c1.cout, n)], nbr3_a, n, res_a=r), c2.cout, n)]
         return x[0]
 
     @torch.no_grad()
@@ -111,29 +143,45 @@ class FusedMinkUNet:
             n = [cm.sets[t].n for t in ts_list]
             nbr3 = [cm.kernel_map(t, t, 3).nbr for t in ts_list]
             down = [cm.kernel_map(ts_list[l], ts_list[l + 1], 2) for l in range(4)]
+            up_nbr = [d.transposed().nbr for d in down]
+            nbr3_a = [t.data_ptr() for t in nbr3]
+
+            arena = torch.empty(self._plan_bytes(n) + 256, dtype=torch.uint8, device=self.device)
+            self._arena = arena                                    # keeps the activations alive until the next forward
+            self._cursor = _al(arena.data_ptr())
+            if self._ws is None:
+                self._ws = torch.empty(96 << 20, dtype=torch.uint8, device=self.device)
+            self._ws_a, self._ws_bytes = self._ws.data_ptr(), self._ws.numel()
+            self._stream = torch.cuda.current_stream().cuda_stream
+            self._fn = C.lib().osb_conv_fwd_tc
 
             cs0 = cm.sets[1].ensure_hash()
-            x_int = torch.empty_like(feats, dtype=torch.float32)
             f32 = feats.float().contiguous()
+            x_int = torch.empty_like(f32)
             C.call('osb_gather_rows_f32', C.ptr(f32), C.ptr(cm.perm), n[0], f32.shape[1], C.ptr(x_int), C.stream_ptr())
             st = self.stem
-            x, _ = tc.conv_stem(x_int, cs0.coords, cs0.slots, cs0.cap, st.ks, 1, st.w3, st.scale, st.shift, True, True, False)
-            skips = [(x, st.cout)]
+            x_a = self._cursor
+            self._cursor += _al(n[0] * 4 * st.cout)
+            C.call('osb_conv_stem_fused', C.ptr(x_int), st.cin, C.ptr(cs0.coords), n[0], C.ptr(cs0.slots), cs0.cap, st.ks, 1,
+                   C.ptr(st.w3), st.cout, st.scale_a, st.shift_a, 1, x_a, None, self._stream)
+            skips = [(x_a, st.cout, n[0])]
             cur = skips[0]
             for l, (dconv, blocks) in enumerate(self.enc):
-                y = self._run(dconv, [cur], down[l].nbr, n[l + 1], relu=True)
-                cur = self._stage(blocks, [(y, dconv.cout)], nbr3[l + 1], n[l + 1])
+                y = self._conv(dconv, [cur], down[l].nbr.data_ptr(), n[l + 1])
+                cur = self._stage(blocks, [(y, dconv.cout, n[l + 1])], nbr3_a[l + 1], n[l + 1])
                 skips.append(cur)
             for j, (uconv, blocks) in enumerate(self.dec):
                 l = 3 - j                                   # output level of this transposed conv
-                y = self._run(uconv, [cur], down[l].transposed().nbr, n[l], relu=True)
-                cur = self._stage(blocks, [(y, uconv.cout), skips[l]], nbr3[l], n[l])
+                y = self._conv(uconv, [cur], up_nbr[l].data_ptr(), n[l])
+                cur = self._stage(blocks, [(y, uconv.cout, n[l]), skips[l]], nbr3_a[l], n[l])
             fin = self.final
-            if fin.wpack is not None:
-                return self._run(fin, [cur], None, n[0], relu=False, out_f32=True, row_map=cm.perm)
-            # odd head width (e.g. 20 classes): generic fp32 kernel, then restore the caller's order
-            xf = tc.from_split(cur[0], cur[1])
             out = torch.empty((n[0], fin.cout), dtype=torch.float32, device=self.device)
+            if fin.wpack is not None:
+                self._conv(fin, [cur], 0, n[0], relu=0, out_f32_a=out.data_ptr(), row_map_a=cm.perm.data_ptr())
+                return out
+            # odd head width (e.g. 20 classes): generic fp32 kernel, then restore the caller's order
+            xf = torch.empty((n[0], cur[1]), dtype=torch.float32, device=self.device)
+            C.call('osb_split_to_f32', cur[0], n[0], cur[1], C.ptr(xf), C.stream_ptr())
             C.call('osb_conv_fwd_f32', C.ptr(xf), fin.cin, None, n[0], 1, C.ptr(fin.w3), fin.cin, fin.cout, 0, C.ptr(out),
                    C.stream_ptr())
             ext = torch.empty_like(out)
