@@ -28,7 +28,7 @@ class CoordSet:
 
     def ensure_hash(self):
         if self.slots is None:
-            self.cap = _next_pow2(max(2 * self.n, 16))
+            self.cap = _next_pow2(max(4 * self.n, 16))      # load factor <= 0.25: short probe chains (the longest of 32 lanes gates a warp)
             self.slots = torch.empty(self.cap * 16, dtype=torch.uint8, device=self.coords.device)
             C.call('osb_hash_build', C.ptr(self.coords), self.n, C.ptr(self.slots), self.cap, C.stream_ptr())
         return self
@@ -74,7 +74,7 @@ class CoordinateManager:
             self.perm = torch.empty(n, dtype=torch.int32, device=dev)
             self.inv_perm = torch.empty(n, dtype=torch.int32, device=dev)
             cs = CoordSet(coords_int, 1)
-            cs.cap = _next_pow2(max(2 * n, 16))
+            cs.cap = _next_pow2(max(4 * n, 16))
             cs.slots = torch.empty(cs.cap * 16, dtype=torch.uint8, device=dev)
             ws_bytes = C.lib().osb_coordset_workspace_bytes(n)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)

@@ -38,66 +38,35 @@ k_conv_stem(const float *__restrict__ in, int cin, const int4 *__restrict__ coor
   for (int64_t o = (int64_t)blockIdx.x * STEM_WARPS + warp; o < n; o += warps_total) {
     const int4 c = __ldg(coords + o);
     float acc = 0.f;
-    // NQ independent probes per lane are in flight at once (first slot of each hash chain, then the neighbour's
-    // features); collisions continue in a rare serial tail.  The hit loop then runs per group of 32 offsets.
-    constexpr int NQ = 4;
-    for (int kb0 = 0; kb0 < K; kb0 += 32 * NQ) {
-      uint64_t key[NQ], slot[NQ];
-      int4 sv[NQ];
-      int row[NQ];
-#pragma unroll
-      for (int u = 0; u < NQ; ++u) {
-        const int k = kb0 + 32 * u + lane;
-        row[u] = -1;
-        key[u] = kEmptyKey;
-        if (k < K) {
-          const int ix = k % ks, iy = (k / ks) % ks, iz = k / (ks * ks);
-          const int dx = ((ks & 1) ? ix - half : ix) * step, dy = ((ks & 1) ? iy - half : iy) * step,
-                    dz = ((ks & 1) ? iz - half : iz) * step;
-          key[u] = pack_key(c.x, c.y + dx, c.z + dy, c.w + dz);
-          slot[u] = hash_u64(key[u]) & mask;
-          sv[u] = __ldg(reinterpret_cast<const int4 *>(slots + slot[u]));
-        }
+    for (int kb = 0; kb < K; kb += 32) {
+      const int k = kb + lane;
+      int row = -1;
+      if (k < K) {
+        const int ix = k % ks, iy = (k / ks) % ks, iz = k / (ks * ks);
+        const int dx = ((ks & 1) ? ix - half : ix) * step, dy = ((ks & 1) ? iy - half : iy) * step,
+                  dz = ((ks & 1) ? iz - half : iz) * step;
+        row = hash_lookup(slots, mask, pack_key(c.x, c.y + dx, c.z + dy, c.w + dz));
       }
-#pragma unroll
-      for (int u = 0; u < NQ; ++u) {
-        if (key[u] == kEmptyKey) continue;
-        while (true) {
-          const uint64_t kk = ((uint64_t)(uint32_t)sv[u].y << 32) | (uint32_t)sv[u].x;
-          if (kk == key[u]) { row[u] = sv[u].z; break; }
-          if (kk == kEmptyKey) break;
-          slot[u] = (slot[u] + 1) & mask;
-          sv[u] = __ldg(reinterpret_cast<const int4 *>(slots + slot[u]));
-        }
+      float4 h = make_float4(0.f, 0.f, 0.f, __int_as_float(k));
+      if (row >= 0) {
+        const float *xp = in + (int64_t)row * cin;
+        h.x = __ldg(xp);
+        if (cin > 1) h.y = __ldg(xp + 1);
+        if (cin > 2) h.z = __ldg(xp + 2);
       }
-      float4 h[NQ];
-#pragma unroll
-      for (int u = 0; u < NQ; ++u) {
-        h[u] = make_float4(0.f, 0.f, 0.f, __int_as_float(kb0 + 32 * u + lane));
-        if (row[u] >= 0) {
-          const float *xp = in + (int64_t)row[u] * cin;
-          h[u].x = __ldg(xp);
-          if (cin > 1) h[u].y = __ldg(xp + 1);
-          if (cin > 2) h[u].z = __ldg(xp + 2);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < NQ; ++u) {
-        if (kb0 + 32 * u >= K) break;                 // warp-uniform
-        const unsigned bal = __ballot_sync(0xffffffffu, row[u] >= 0);
-        if (row[u] >= 0) s_hit[warp][__popc(bal & ((1u << lane) - 1))] = h[u];
-        __syncwarp();
-        const int nhit = __popc(bal);
+      const unsigned bal = __ballot_sync(0xffffffffu, row >= 0);
+      if (row >= 0) s_hit[warp][__popc(bal & ((1u << lane) - 1))] = h;
+      __syncwarp();
+      const int nhit = __popc(bal);
 #pragma unroll 4
-        for (int j = 0; j < nhit; ++j) {
-          const float4 hv = s_hit[warp][j];                               // broadcast
-          const float4 wv = s_w4[(__float_as_int(hv.w) << 5) + lane];     // conflict-free
-          acc = fmaf(hv.x, wv.x, acc);
-          acc = fmaf(hv.y, wv.y, acc);
-          acc = fmaf(hv.z, wv.z, acc);
-        }
-        __syncwarp();
+      for (int j = 0; j < nhit; ++j) {
+        const float4 hv = s_hit[warp][j];                               // broadcast
+        const float4 wv = s_w4[(__float_as_int(hv.w) << 5) + lane];     // conflict-free
+        acc = fmaf(hv.x, wv.x, acc);
+        acc = fmaf(hv.y, wv.y, acc);
+        acc = fmaf(hv.z, wv.z, acc);
       }
+      __syncwarp();
     }
     if (lane < cout) {
       float y = fmaf(acc, sc, sh);

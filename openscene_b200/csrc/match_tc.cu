@@ -7,10 +7,10 @@
 // between the 3-D and the fused 2-D feature (ensemble select).  The operands are rounded to fp16 exactly where the
 // reference rounds them, so the [N_pts, C] x [C, K] product is the reference's own fp16 GEMM.
 //
-// One CTA = 128 points.  Warps 0-7 build the A operand: one warp per row at a time, the row lives in registers
+// One CTA = 128 points.  Warps 0-15 build the A operand: one warp per row at a time, the row lives in registers
 // (coalesced 256-byte loads), is reduced for the norm, rounded to fp16 and written into the K-major 128B-swizzled
-// shared-memory tile of all C/64 depth chunks (192 KB for C = 768).  Warp 8 streams the text matrix chunk by chunk with
-// TMA (rows >= K_text are out of bounds -> zero fill), warp 9 issues `tcgen05.mma kind::f16` (M=128, N<=96 per pass,
+// shared-memory tile of all C/64 depth chunks (192 KB for C = 768).  Warp 16 streams the text matrix chunk by chunk with
+// TMA (rows >= K_text are out of bounds -> zero fill), warp 17 issues `tcgen05.mma kind::f16` (M=128, N<=96 per pass,
 // K=16), warps 0-3 read the accumulators from TMEM, round to fp16, take the first-maximum argmax and write
 // scores / labels / row maxima.  HBM-bound: 4*C (or 2*C) bytes per point against 2*C*K flops.
 #include "tc_ptx.cuh"
@@ -20,7 +20,8 @@ namespace osb {
 
 constexpr int MT_M = 128;
 constexpr int MT_NW = 96;            // text rows per MMA pass (N of the instruction)
-constexpr int MT_THREADS = 320;      // 8 A-producer warps + TMA warp + MMA warp
+constexpr int MT_PW = 16;             // A-producer warps (8 rows each)
+constexpr int MT_THREADS = (MT_PW + 2) * 32;   // + TMA warp + MMA warp
 constexpr int MT_BSTAGES = 2;
 
 struct MatchTcParams {
@@ -59,33 +60,34 @@ k_match_tc(const __grid_constant__ CUtensorMap tmT, const MatchTcParams p) {
 
   if (tid == 0) {
     for (int s = 0; s < MT_BSTAGES; ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, 1); }
-    mbar_init(a_full, 256);
+    mbar_init(a_full, MT_PW * 32);
     mbar_init(accum, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 9) {
+  if (warp == MT_PW + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_misc[0])), "r"((uint32_t)p.tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  if (tid == 8 * 32) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmT) : "memory");
+  if (tid == MT_PW * 32) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmT) : "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = s_misc[0];
   const int n_stage = p.n_pass * NP;
 
-  if (warp < 8) {
-    // ============================ A producers: 16 rows per warp =============================
-    // RB rows are in flight per warp (loads of all RB rows are issued before any is consumed): 8 warps x RB x 3 KB
-    // of outstanding loads per SM is what it takes to keep HBM busy from one CTA per SM.
-    constexpr int RB = 4;
-    for (int rr0 = 0; rr0 < 16; rr0 += RB) {
+  if (warp < MT_PW) {
+    // ============================ A producers: 8 rows per warp ==============================
+    // RB rows are in flight per warp (their loads are issued before any is consumed): 16 warps x RB x 3 KB of
+    // outstanding loads per SM keeps HBM busy from the single resident CTA; 16 warps also spread the
+    // convert / normalise instruction stream over all four schedulers.
+    constexpr int RB = 2, ROWS_PW = MT_M / MT_PW;
+    for (int rr0 = 0; rr0 < ROWS_PW; rr0 += RB) {
       float v[RB][2 * NP];
       bool f16[RB], live[RB];
       float ss[RB];
 #pragma unroll
       for (int u = 0; u < RB; ++u) {
-        const int64_t pt = row0 + warp * 16 + rr0 + u;
+        const int64_t pt = row0 + warp * ROWS_PW + rr0 + u;
         live[u] = pt < p.n_pts;
         f16[u] = false;
         ss[u] = 0.f;
@@ -117,7 +119,7 @@ k_match_tc(const __grid_constant__ CUtensorMap tmT, const MatchTcParams p) {
       }
 #pragma unroll
       for (int u = 0; u < RB; ++u) {
-        const int r = warp * 16 + rr0 + u;
+        const int r = warp * ROWS_PW + rr0 + u;
         const int64_t pt = row0 + r;
         if (p.normalize) {
 #pragma unroll
@@ -132,8 +134,11 @@ k_match_tc(const __grid_constant__ CUtensorMap tmT, const MatchTcParams p) {
           } else {
             d = nrm + 1e-5f;
           }
+          // x / d evaluated as x * (1/d) (one rounding more than the reference's division; the following fp16
+          // rounding absorbs it except for values within 2^-24 of an fp16 rounding boundary)
+          const float rd = __frcp_rn(d);
 #pragma unroll
-          for (int j = 0; j < 2 * NP; ++j) v[u][j] = v[u][j] / d;
+          for (int j = 0; j < 2 * NP; ++j) v[u][j] = v[u][j] * rd;
         }
         // chunk j of this row: lane holds elements 2*lane, 2*lane+1 -> bytes [4*lane, 4*lane+4) of the 128-byte line
         const uint32_t line = smem_u32(sA) + r * 128 + ((((4 * lane) >> 4) ^ (r & 7)) << 4) + ((4 * lane) & 15);
@@ -148,7 +153,7 @@ k_match_tc(const __grid_constant__ CUtensorMap tmT, const MatchTcParams p) {
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");           // generic-proxy writes -> UMMA reads
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a_full) : "memory");
-  } else if (warp == 8) {
+  } else if (warp == MT_PW) {
     // ============================ TMA producer: text chunks ==================================
     int s = 0; uint32_t phase = 0;
     for (int t = 0; t < n_stage; ++t) {
@@ -216,7 +221,7 @@ k_match_tc(const __grid_constant__ CUtensorMap tmT, const MatchTcParams p) {
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols));
+  if (warp == MT_PW + 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols));
 }
 
 static int launch_match_tc(const MatchTcParams &p, const void *text_f16, cudaStream_t stream) {
