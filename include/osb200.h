@@ -122,6 +122,10 @@ int osb_conv_wgrad_f32(const float *in, const int32_t *nbr, int64_t n_out, int32
  *   out_split   split rows [n_out, cout] or NULL
  *   out_f32     fp32 [n_out, cout] or NULL; out_row_map (int32 [n_out] or NULL) scatters fp32 rows:
  *               row o is written to out_f32[out_row_map[o]]
+ *   flags       bit0: launch with programmatic stream serialization (PDL).  The kernel's prologue (barrier / TMEM
+ *               set-up, loading `nbr`, scale, shift) then overlaps the tail of the previous kernel in `stream`; it
+ *               waits for that kernel before touching src*, res, ws or any output.  Only legal when nbr / wpack /
+ *               scale / shift were NOT produced by the immediately preceding kernel in the stream.
  */
 size_t osb_conv_packed_weight_bytes(int32_t K, int32_t cin, int32_t cout);
 /* Scratch osb_conv_fwd_tc needs for this shape: small problems are split over the (offset, channel-block)
@@ -132,7 +136,7 @@ int osb_conv_pack_weights(const float *w, int32_t K, int32_t cin, int32_t cout, 
 int osb_conv_fwd_tc(const void *src0, int32_t c0, int64_t n_src0, const void *src1, int32_t c1, int64_t n_src1,
                     const int32_t *nbr, int64_t n_out, int32_t K, const void *wpack, int32_t cout,
                     const float *scale, const float *shift, const void *res, int32_t relu, void *out_split,
-                    float *out_f32, const int32_t *out_row_map, void *ws, size_t ws_bytes, void *stream);
+                    float *out_f32, const int32_t *out_row_map, void *ws, size_t ws_bytes, int32_t flags, void *stream);
 
 /* Stem: fused kernel-map probe + conv for tiny cin (<= 3) and cout <= 32, fp32 FMA.  One launch replaces the
  * 5x5x5 map build (125 probes / voxel) and the 3->32 convolution of `conv0p1s1`.

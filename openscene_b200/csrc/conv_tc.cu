@@ -49,6 +49,7 @@ struct ConvTcParams {
   float *partial;        // [nsplit][n_out][cout_pad] raw accumulators (nsplit > 1)
   const uint8_t *src0_ptr, *src1_ptr;   // raw bases (L2 prefetch of a later tile's own rows)
   int pf_dist;           // tiles ahead to prefetch into L2 (0 = off; only when input rows == output rows)
+  int pdl;               // launched with programmatic stream serialization (see osb_conv_fwd_tc flags)
   int dbg_skip;          // tuning only: bit0 = no A gathers, bit1 = no B loads, bit2 = no main loop, bit3 = no stores
   long long *dbg_clock;  // tuning only: per-CTA timestamps [gridDim.x][8] (may be NULL)
 };
@@ -68,6 +69,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
   uint32_t *s_misc = reinterpret_cast<uint32_t *>(bars + 17);               // [0] tmem base, [1] kmask
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (p.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel may start its prologue
   if (p.dbg_clock && tid == 64) { p.dbg_clock[blockIdx.x * 8 + 0] = clock64(); unsigned sm; asm("mov.u32 %0, %%smid;" : "=r"(sm)); p.dbg_clock[blockIdx.x * 8 + 7] = sm; }
   const int64_t row0 = (int64_t)blockIdx.x * TC_M;
   const int n0 = blockIdx.y * p.nt;
@@ -127,6 +129,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  // Everything above touched only launch-invariant data (kernel map, BN constants).  The activations, the residual
+  // and the shared split workspace belong to the previous kernel in the stream: wait for it to finish and flush.
+  if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t tmem_base = s_misc[0];
   const uint32_t kmask = (p.dbg_skip & 4) ? 0u : s_misc[1];
   if (p.dbg_clock && tid == 64) p.dbg_clock[blockIdx.x * 8 + 1] = clock64();
@@ -408,7 +413,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
 __global__ void k_conv_finish(const float *__restrict__ partial, int nsplit, int64_t n_out, int cout, int cout_pad,
                               const float *__restrict__ scale, const float *__restrict__ shift,
                               const uint8_t *__restrict__ res, int relu, uint8_t *__restrict__ out_split,
-                              float *__restrict__ out_f32, const int32_t *__restrict__ out_row_map) {
+                              float *__restrict__ out_f32, const int32_t *__restrict__ out_row_map, int pdl) {
+  if (pdl) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");           // partials come from the k_conv_tc launch just before
+  }
   const int groups = cout / 8;
   const int64_t total = n_out * groups;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -560,7 +569,7 @@ int osb_conv_pack_weights(const float *w, int32_t K, int32_t cin, int32_t cout, 
 int osb_conv_fwd_tc(const void *src0, int32_t c0, int64_t n_src0, const void *src1, int32_t c1, int64_t n_src1,
                     const int32_t *nbr, int64_t n_out, int32_t K, const void *wpack, int32_t cout, const float *scale,
                     const float *shift, const void *res, int32_t relu, void *out_split, float *out_f32,
-                    const int32_t *out_row_map, void *ws, size_t ws_bytes, void *stream_) {
+                    const int32_t *out_row_map, void *ws, size_t ws_bytes, int32_t flags, void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   OSB_CHECK(src0 && c0 > 0 && c0 % 32 == 0 && c1 >= 0 && c1 % 32 == 0, "osb_conv_fwd_tc: channel counts must be multiples of 32 (c0=%d c1=%d)", c0, c1);
   OSB_CHECK((c1 == 0) == (src1 == nullptr), "osb_conv_fwd_tc: src1 / c1 mismatch");
@@ -596,6 +605,7 @@ int osb_conv_fwd_tc(const void *src0, int32_t c0, int64_t n_src0, const void *sr
   p.out_split = (uint8_t *)out_split; p.out_f32 = out_f32; p.out_row_map = out_row_map;
   p.use_gather4 = g_tc_use_gather4;
   p.dbg_skip = g_tc_dbg_skip;
+  p.pdl = (flags & 1) ? 1 : 0;
   p.dbg_clock = g_tc_dbg_clock;
   p.src0_ptr = (const uint8_t *)src0; p.src1_ptr = (const uint8_t *)src1;
   p.pf_dist = (n_src0 == n_out && (c1 == 0 || n_src1 == n_out) && (K & 1)) ? g_tc_pf_dist : 0;
@@ -614,13 +624,22 @@ int osb_conv_fwd_tc(const void *src0, int32_t c0, int64_t n_src0, const void *sr
     configured = 227 * 1024;
   }
   dim3 grid((unsigned)ceil_div(n_out, TC_M), (unsigned)(cp / p.nt), (unsigned)p.nsplit);
-  k_conv_tc<<<grid, TC_THREADS, smem_bytes, stream>>>(tmA0, tmA1, tmB, p);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
+  cfg.attrs = attr; cfg.numAttrs = p.pdl ? 1 : 0;
+  OSB_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc, tmA0, tmA1, tmB, p));
   OSB_LAUNCH_CHECK();
   if (p.nsplit > 1) {
     const int64_t total = n_out * (cout / 8);
     const unsigned fgrid = (unsigned)std::min<int64_t>(ceil_div(total, 256), 148 * 8);
-    k_conv_finish<<<fgrid, 256, 0, stream>>>(p.partial, p.nsplit, n_out, cout, cp, scale, shift, (const uint8_t *)res, relu,
-                                            (uint8_t *)out_split, out_f32, out_row_map);
+    cudaLaunchConfig_t fcfg{};
+    fcfg.gridDim = dim3(fgrid); fcfg.blockDim = dim3(256); fcfg.dynamicSmemBytes = 0; fcfg.stream = stream;
+    fcfg.attrs = attr; fcfg.numAttrs = p.pdl ? 1 : 0;
+    OSB_CUDA(cudaLaunchKernelEx(&fcfg, k_conv_finish, (const float *)p.partial, p.nsplit, n_out, (int)cout, cp, scale, shift,
+                                (const uint8_t *)res, (int)relu, (uint8_t *)out_split, out_f32, out_row_map, p.pdl));
     OSB_LAUNCH_CHECK();
   }
   return 0;

@@ -74,6 +74,8 @@ class FusedMinkUNet:
         self.out_channels = self.final.cout
         self.last_cm = None
         self._ws = None
+        import os
+        self.use_pdl = os.environ.get('OSB_PDL', '1') != '0'
 
     @staticmethod
     def _blocks(seq):
@@ -113,7 +115,7 @@ class FusedMinkUNet:
             out_a = self._cursor
             self._cursor += _al(n_out * 4 * cv.cout)
         rc = self._fn(s0, c0, r0, s1, c1, r1, nbr_a, n_out, cv.K, cv.wpack_a, cv.cout, cv.scale_a, cv.shift_a, res_a, relu,
-                      out_a, out_f32_a, row_map_a, self._ws_a, self._ws_bytes, self._stream)
+                      out_a, out_f32_a, row_map_a, self._ws_a, self._ws_bytes, self._flags, self._stream)
         if rc:
             C.check(rc, 'osb_conv_fwd_tc')
         return out_a
@@ -154,6 +156,9 @@ class FusedMinkUNet:
             self._ws_a, self._ws_bytes = self._ws.data_ptr(), self._ws.numel()
             self._stream = torch.cuda.current_stream().cuda_stream
             self._fn = C.lib().osb_conv_fwd_tc
+            # PDL: every kernel map / packed weight / BN constant is complete before the chain starts (maps are built
+            # above, the stem kernel sits between them and the first convolution)
+            self._flags = 1 if self.use_pdl else 0
 
             cs0 = cm.sets[1].ensure_hash()
             f32 = feats.float().contiguous()

@@ -56,7 +56,7 @@ def conv_tc(src0, c0, src1, c1, nbr, n_out, K, wpack, cout, scale=None, shift=No
     ws = _workspace(dev, ws_bytes) if ws_bytes else None
     C.call('osb_conv_fwd_tc', C.ptr(src0), c0, src0.shape[0], C.ptr(src1), c1, 0 if src1 is None else src1.shape[0],
            C.ptr(nbr), n_out, K, C.ptr(wpack), cout, C.ptr(scale), C.ptr(shift), C.ptr(res), int(relu),
-           C.ptr(os_), C.ptr(of_), C.ptr(out_row_map), C.ptr(ws), ws_bytes, C.stream_ptr())
+           C.ptr(os_), C.ptr(of_), C.ptr(out_row_map), C.ptr(ws), ws_bytes, 0, C.stream_ptr())
     return os_, of_
 
 
