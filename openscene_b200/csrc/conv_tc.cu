@@ -517,13 +517,22 @@ static int g_tc_dbg_skip = 0;
 static int g_tc_force_split = 0;            // 0 = heuristic, >0 = forced nsplit (1 disables)
 static int g_tc_target_ctas = 148;          // split small launches until ~one CTA per SM (sweep: profiles/r01_tune_conv.md)
 static int g_tc_pf_dist = 0;
+static int g_tc_small_nt = 0;              // > 0: N tile used when the launch has few row tiles (tuning)
+static int g_tc_small_rows = 5120;
 static long long *g_tc_dbg_clock = nullptr;
 
 }  // namespace osb
 
 using namespace osb;
 
+static inline int choose_nt(int64_t n_out, int cp);
 static inline int cout_pad_of(int cout) { return cout <= 256 ? (cout + 15) / 16 * 16 : (cout + 255) / 256 * 256; }
+
+static inline int choose_nt(int64_t n_out, int cp) {
+  int nt = cp <= 256 ? cp : 256;
+  if (g_tc_small_nt > 0 && n_out <= g_tc_small_rows && nt > g_tc_small_nt && cp % g_tc_small_nt == 0) nt = g_tc_small_nt;
+  return nt;
+}
 
 extern "C" {
 
@@ -533,6 +542,7 @@ void osb_debug_set_tc(int use_gather4, int smem_budget) {
   if (smem_budget > 0) g_tc_smem_budget = smem_budget;
 }
 void osb_debug_set_tc3(int pf_dist) { g_tc_pf_dist = pf_dist; }
+void osb_debug_set_tc4(int small_nt, int small_rows) { g_tc_small_nt = small_nt; if (small_rows > 0) g_tc_small_rows = small_rows; }
 void osb_debug_set_clock(void *buf) { g_tc_dbg_clock = (long long *)buf; }
 void osb_debug_set_tc2(int dbg_skip, int force_split, int target_ctas) {
   if (dbg_skip >= 0) g_tc_dbg_skip = dbg_skip;
@@ -543,7 +553,7 @@ void osb_debug_set_tc2(int dbg_skip, int force_split, int target_ctas) {
 // bytes of caller-provided scratch osb_conv_fwd_tc may need for this shape (0 = none)
 size_t osb_conv_tc_workspace_bytes(int64_t n_out, int32_t K, int32_t cin, int32_t cout) {
   const int cp = cout_pad_of(cout);
-  const int nt = cp <= 256 ? cp : 256;
+  const int nt = choose_nt(n_out, cp);
   const int64_t ctas = ceil_div(n_out, TC_M) * (cp / nt);
   int nsplit = g_tc_force_split > 0 ? g_tc_force_split : (int)(g_tc_target_ctas / ctas);
   nsplit = std::max(1, std::min(nsplit, std::min(32, K * (cin / 32))));
@@ -581,7 +591,7 @@ int osb_conv_fwd_tc(const void *src0, int32_t c0, int64_t n_src0, const void *sr
   const int cin = c0 + c1;
   const int cp = cout_pad_of(cout);
   ConvTcParams p{};
-  p.nt = cp <= 256 ? cp : 256;
+  p.nt = choose_nt(n_out, cp);
   const int stage_bytes = TC_A_BYTES + p.nt * 128;
   const int aux_bytes = K * TC_M * 4 + 2 * 256 * 4 + 17 * 8 + 64;
   int stages = (g_tc_smem_budget - 1024 - aux_bytes) / stage_bytes;      // two CTAs per SM if that leaves >= 3 stages

@@ -46,11 +46,20 @@ def case(level, cin, cout, ks, label, **dbg):
     tc.debug_set_tc(**dbg)
     f32 = cout > 256
     us = timeit(lambda: tc.conv_tc(x, cin, None, 0, nbr, n, K, w, cout, None, None, None, True, not f32, f32, None))
-    tc.debug_set_tc(use_gather4=2, smem_budget=112 * 1024, dbg_skip=0, force_split=0, target_ctas=296, pf_dist=296)
+    tc.debug_set_tc(use_gather4=2, smem_budget=112 * 1024, dbg_skip=0, force_split=0, target_ctas=148, pf_dist=0, small_nt=0)
     print(f'{label:46s} L{level} n={n:7d} {cin:3d}->{cout:3d} k{ks}  {us:9.1f} us', flush=True)
 
 
 B2, B1 = 112 * 1024, 226 * 1024
+if len(sys.argv) > 2 and sys.argv[2] == 'small':
+    for lvl in (2, 3, 4):
+        c = {2: 128, 3: 256, 4: 256}[lvl]
+        for snt in (0, 128, 64):
+            for tgt in (148, 296):
+                case(lvl, c, c, 3, f'L{lvl} small_nt={snt} target={tgt}', small_nt=snt, target_ctas=tgt)
+        case(lvl, c, c, 1, f'L{lvl} 1x1 small_nt=0', small_nt=0)
+        case(lvl, c, c, 1, f'L{lvl} 1x1 small_nt=64', small_nt=64)
+    sys.exit(0)
 if len(sys.argv) > 2 and sys.argv[2] == 'pf':
     for hot in (False, True):
         HOT = hot
