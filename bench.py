@@ -219,8 +219,9 @@ def main():
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); fn(); b.record()
             evs.append((a, b))
-            if sampler is not None and i % 4 == 1:
+            if sampler is not None and i in (k // 4, k // 2, (3 * k) // 4):
                 sampler.sample()                                     # GPU still busy with this step; outside its event pair
+                                                                     # (each NVML query stalls the CPU for ms: keep them few)
         torch.cuda.synchronize()
         return sum(a.elapsed_time(b) for a, b in evs)
 
@@ -302,8 +303,13 @@ def main():
         }
         if not args.modules:
             ach = conv_bytes / (conv_ms * 1e-3) / 1e9
+            traffic = None
+            tpath = os.path.join(ROOT, 'profiles', 'traffic.json')     # dram bytes per launch from the committed ncu --set full capture
+            if os.path.exists(tpath):
+                traffic = json.load(open(tpath))
             line['roofline'] = {'bound': 'hbm', 'kernel': 'k_conv_tc', 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
-                                'frac': ach / peak, 'traffic': None, 'peak_source': peak_src,
+                                'frac': ach / peak, 'traffic': traffic['dram_bytes_per_launch'] if traffic else None,
+                                'traffic_note': traffic['note'] if traffic else None, 'peak_source': peak_src,
                                 'launches_per_step': conv_calls, 'kernel_ms_per_step': conv_ms,
                                 'algorithmic_bytes_per_step': conv_bytes, 'tflops': conv_flops / (conv_ms * 1e-3) / 1e12,
                                 'step_algorithmic_bytes': all_bytes, 'step_gflop': all_flops / 1e9}
