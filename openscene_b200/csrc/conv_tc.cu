@@ -311,14 +311,19 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
     const int sw = lane & 7;
     // staged tile -> global: dst_row(r) gives the destination row index of tile row r (or -1)
     auto flush_tile = [&](uint8_t *base, int64_t row_bytes, int64_t col_byte, bool mapped) {
+      uint4 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {                 // all shared loads first, then all global stores
+        const int r = 4 * i + rsub;
+        v[i] = lds128(stg + r * 128 + ((chunk ^ (r & 7)) << 4));
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = 4 * i + rsub;
-        const uint4 v = lds128(stg + r * 128 + ((chunk ^ (r & 7)) << 4));
         const int32_t mo = __shfl_sync(0xffffffffu, my_orow, r);
         const int64_t grow = mapped ? (int64_t)mo : wrow0 + r;
         if (wrow0 + r < p.n_out && !no_store)
-          *reinterpret_cast<uint4 *>(base + grow * row_bytes + col_byte + chunk * 16) = v;
+          *reinterpret_cast<uint4 *>(base + grow * row_bytes + col_byte + chunk * 16) = v[i];
       }
     };
     for (int cbo = 0; cbo < p.nt / 32; ++cbo) {
@@ -348,8 +353,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
         continue;
       }
       if (c0 >= p.cout) continue;               // warp-uniform
+      if (p.scale != nullptr) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) y[j] = fmaf(y[j], s_scale[cbo * 32 + j], s_shift[cbo * 32 + j]);
+        for (int j = 0; j < 32; ++j) y[j] = fmaf(y[j], s_scale[cbo * 32 + j], s_shift[cbo * 32 + j]);
+      }
       if (p.res) {                               // residual tile: coalesced load -> smem -> own row
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -588,15 +595,18 @@ int osb_conv_fwd_tc(const void *src0, int32_t c0, int64_t n_src0, const void *sr
   OSB_CHECK(n_out > 0 && n_src0 > 0 && n_src0 < (1ll << 31) && n_src1 < (1ll << 31), "osb_conv_fwd_tc: bad row counts");
   OSB_CHECK(cout % 32 == 0 && cout > 0, "osb_conv_fwd_tc: cout (%d) must be a multiple of 32", cout);
   OSB_CHECK(out_split || out_f32, "osb_conv_fwd_tc: no output given");
+  OSB_CHECK((scale == nullptr) == (shift == nullptr), "osb_conv_fwd_tc: scale and shift go together");
   const int cin = c0 + c1;
   const int cp = cout_pad_of(cout);
   ConvTcParams p{};
   p.nt = choose_nt(n_out, cp);
   const int stage_bytes = TC_A_BYTES + p.nt * 128;
   const int aux_bytes = K * TC_M * 4 + 2 * 256 * 4 + 17 * 8 + 64;
-  int stages = (g_tc_smem_budget - 1024 - aux_bytes) / stage_bytes;      // two CTAs per SM if that leaves >= 3 stages
-  if (stages < 3) stages = (226 * 1024 - 1024 - aux_bytes) / stage_bytes;
-  stages = std::max(2, std::min(8, stages));
+  const int seq = K * (cin / 32);                                         // stages one tile runs through (upper bound)
+  int stages = (g_tc_smem_budget - 1024 - aux_bytes) / stage_bytes;      // two CTAs per SM if that leaves >= 3 stages ...
+  if (stages < 3 && !(stages == 2 && seq <= 4))                          // ... or the whole sequence is that short anyway
+    stages = (226 * 1024 - 1024 - aux_bytes) / stage_bytes;
+  stages = std::max(2, std::min(8, std::min(stages, std::max(2, seq))));
   const size_t smem_bytes = (size_t)stages * stage_bytes + aux_bytes + 1024;
   OSB_CHECK(smem_bytes <= 227 * 1024, "osb_conv_fwd_tc: tile does not fit in shared memory");
   int tmem_cols = 32;
