@@ -526,6 +526,7 @@ static int g_tc_target_ctas = 148;          // split small launches until ~one C
 static int g_tc_pf_dist = 0;
 static int g_tc_small_nt = 0;              // > 0: N tile used when the launch has few row tiles (tuning)
 static int g_tc_small_rows = 5120;
+static int g_tc_min_stages = 3;            // fewest stages accepted for the multi-CTA-per-SM configuration
 static long long *g_tc_dbg_clock = nullptr;
 
 }  // namespace osb
@@ -550,6 +551,7 @@ void osb_debug_set_tc(int use_gather4, int smem_budget) {
 }
 void osb_debug_set_tc3(int pf_dist) { g_tc_pf_dist = pf_dist; }
 void osb_debug_set_tc4(int small_nt, int small_rows) { g_tc_small_nt = small_nt; if (small_rows > 0) g_tc_small_rows = small_rows; }
+void osb_debug_set_tc5(int min_stages) { g_tc_min_stages = min_stages; }
 void osb_debug_set_clock(void *buf) { g_tc_dbg_clock = (long long *)buf; }
 void osb_debug_set_tc2(int dbg_skip, int force_split, int target_ctas) {
   if (dbg_skip >= 0) g_tc_dbg_skip = dbg_skip;
@@ -604,7 +606,7 @@ int osb_conv_fwd_tc(const void *src0, int32_t c0, int64_t n_src0, const void *sr
   const int aux_bytes = K * TC_M * 4 + 2 * 256 * 4 + 17 * 8 + 64;
   const int seq = K * (cin / 32);                                         // stages one tile runs through (upper bound)
   int stages = (g_tc_smem_budget - 1024 - aux_bytes) / stage_bytes;      // two CTAs per SM if that leaves >= 3 stages ...
-  if (stages < 3 && !(stages == 2 && seq <= 4))                          // ... or the whole sequence is that short anyway
+  if (stages < g_tc_min_stages && !(stages == 2 && seq <= 4))            // ... or the whole sequence is that short anyway
     stages = (226 * 1024 - 1024 - aux_bytes) / stage_bytes;
   stages = std::max(2, std::min(8, std::min(stages, std::max(2, seq))));
   const size_t smem_bytes = (size_t)stages * stage_bytes + aux_bytes + 1024;

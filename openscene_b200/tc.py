@@ -70,7 +70,7 @@ def conv_stem(x, coords, slots, cap, ks, step, w3, scale=None, shift=None, relu=
     return os_, of_
 
 
-def debug_set_tc(use_gather4=-1, smem_budget=0, dbg_skip=-1, force_split=-1, target_ctas=0, pf_dist=None, small_nt=None):
+def debug_set_tc(use_gather4=-1, smem_budget=0, dbg_skip=-1, force_split=-1, target_ctas=0, pf_dist=None, small_nt=None, min_stages=None):
     fn = C.lib().osb_debug_set_tc
     fn.restype, fn.argtypes = None, [ctypes.c_int, ctypes.c_int]
     fn(use_gather4, smem_budget)
@@ -85,6 +85,10 @@ def debug_set_tc(use_gather4=-1, smem_budget=0, dbg_skip=-1, force_split=-1, tar
         fn4 = C.lib().osb_debug_set_tc4
         fn4.restype, fn4.argtypes = None, [ctypes.c_int, ctypes.c_int]
         fn4(small_nt, 0)
+    if min_stages is not None:
+        fn5 = C.lib().osb_debug_set_tc5
+        fn5.restype, fn5.argtypes = None, [ctypes.c_int]
+        fn5(min_stages)
 
 
 def debug_set_clock(buf):
