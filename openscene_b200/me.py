@@ -211,15 +211,33 @@ def _conv_raw(x, kmap, w3, n_out, transpose_w=False):
     return out
 
 
+def _tc_ok(cin, cout, K):
+    return cin % 32 == 0 and cout % 32 == 0 and K <= 32 and _module_tc_enabled()
+
+
+def _conv_tc_f32(x, kmap, wpack, cin, cout, K, n_out):
+    """fp32 rows in, fp32 rows out through the tcgen05 kernel (bf16x3 split operands)."""
+    from . import tc
+    xs = tc.to_split(x)
+    nbr = kmap.nbr if kmap is not None else None
+    return tc.conv_tc(xs, cin, None, 0, nbr, n_out, K, wpack, cout, out_split=False, out_f32=True)[1]
+
+
 class SparseConvFunction(torch.autograd.Function):
     """Forward / dgrad / wgrad of the generalised sparse convolution on libosb200 kernels
-    (replaces MinkowskiConvolutionFunction / ...TransposeFunction inside MinkowskiEngine)."""
+    (replaces MinkowskiConvolutionFunction / ...TransposeFunction inside MinkowskiEngine).
+    Forward and dgrad run on the tcgen05 kernel when the channel counts are multiples of 32 (dgrad = the same
+    kernel on the transposed map with W^T packed); wgrad and odd shapes use the exact-fp32 CUDA-core kernels."""
 
     @staticmethod
     def forward(ctx, x, w3, kmap, n_out):
         ctx.kmap, ctx.n_in = kmap, x.shape[0]
         ctx.save_for_backward(x, w3)
+        K, cin, cout = w3.shape
         with torch.cuda.device(x.device):
+            if _tc_ok(cin, cout, K) and x.dtype == torch.float32:
+                from . import tc
+                return _conv_tc_f32(x.contiguous(), kmap, tc.pack_weights(w3), cin, cout, K, n_out)
             return _conv_raw(x, kmap, w3, n_out)
 
     @staticmethod
@@ -228,13 +246,17 @@ class SparseConvFunction(torch.autograd.Function):
         kmap = ctx.kmap
         gout = gout.contiguous()
         gx = gw = None
+        K, cin, cout = w3.shape
         with torch.cuda.device(x.device):
             if ctx.needs_input_grad[0]:
                 kt = kmap.transposed() if kmap is not None else None
-                gx = _conv_raw(gout, kt, w3, ctx.n_in, transpose_w=True)
+                if _tc_ok(cin, cout, K) and gout.dtype == torch.float32:
+                    from . import tc
+                    gx = _conv_tc_f32(gout, kt, tc.pack_weights(w3, transpose_w=True), cout, cin, K, ctx.n_in)
+                else:
+                    gx = _conv_raw(gout, kt, w3, ctx.n_in, transpose_w=True)
             if ctx.needs_input_grad[1]:
                 gw = torch.empty_like(w3)
-                K, cin, cout = w3.shape
                 nbr = kmap.nbr if kmap is not None else None
                 C.call('osb_conv_wgrad_f32', C.ptr(x.contiguous()), C.ptr(nbr), gout.shape[0], K, C.ptr(gout),
                        cin, cout, C.ptr(gw), C.stream_ptr())
