@@ -154,3 +154,40 @@ print('OK')
     r = subprocess.run([sys.executable, '-c', src], capture_output=True, text=True, timeout=240)
     print(r.stdout[-2000:], r.stderr[-3000:])
     assert r.returncode == 0 and 'OK' in r.stdout
+
+
+def test_tc_autograd_forward_and_dgrad_match_oracle():
+    """SparseConvFunction on 32-multiple channels: forward and dgrad run on the tcgen05 kernel (dgrad = the same
+    kernel on the transposed map with W^T packed), wgrad on the fp32 kernel.  Against the fp64 oracle's autograd."""
+    src = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, %(root)r)
+from openscene_b200 import me, synth
+from oracle import me_cpu
+dev = 'cuda:0'
+c = synth.scene('tiny')
+torch.manual_seed(3)
+f = torch.randn(len(c), 32)
+fo = f.clone().double().requires_grad_(True)
+fg = f.clone().to(dev).requires_grad_(True)
+specs = [('c', 32, 64, 3, 1), ('c', 64, 64, 2, 2), ('c', 64, 96, 1, 1), ('t', 96, 32, 2, 2)]
+mk = lambda M: [ (M.MinkowskiConvolution if k == 'c' else M.MinkowskiConvolutionTranspose)(i, o, kernel_size=ks, stride=st, dimension=3) for k, i, o, ks, st in specs]
+no, ng = mk(me_cpu), mk(me)
+for a, b in zip(no, ng):
+    b.load_state_dict(a.state_dict()); a.double(); b.to(dev)
+xo = me_cpu.SparseTensor(fo, torch.from_numpy(c)); xg = me.SparseTensor(fg, torch.from_numpy(c).to(dev))
+for m in no: xo = m(xo)
+for m in ng: xg = m(xg)
+w = torch.randn(len(c), 32, generator=torch.Generator().manual_seed(9))
+(xo.F * w.double()).sum().backward(); (xg.F * w.to(dev)).sum().backward()
+rel = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())
+e_out = rel(xg.F.detach().cpu().numpy(), xo.F.detach().numpy())
+e_gx = rel(fg.grad.cpu().numpy(), fo.grad.numpy())
+e_gw = max(rel(b.kernel.grad.cpu().numpy(), a.kernel.grad.numpy()) for a, b in zip(no, ng))
+print('err out %%.2e gx %%.2e gw %%.2e' %% (e_out, e_gx, e_gw))
+assert e_out < 1e-4 and e_gx < 1e-4 and e_gw < 1e-4
+print('OK')
+''' % {'root': ROOT}
+    r = subprocess.run([sys.executable, '-c', src], capture_output=True, text=True, timeout=240)
+    print(r.stdout[-2000:], r.stderr[-3000:])
+    assert r.returncode == 0 and 'OK' in r.stdout

@@ -29,40 +29,47 @@ def test_forward_matches_reference_golden(arch):
 
 def test_train_mode_batchnorm_and_backward_match_oracle():
     """distill.py runs the net in train mode (BN batch statistics) and back-propagates a cosine loss.
-    Truth = fp64 oracle; yardstick = the fp32 oracle (reference precision): train-mode BN over the few
-    voxels of the coarse levels is ill-conditioned, so the GPU error is bounded by a multiple of it."""
+    Truth = fp64 oracle.  Train-mode BN over the handful of voxels of the coarse levels is ill-conditioned, so the
+    yardstick for the gradients is the fp64 oracle itself with every conv kernel perturbed by 2^-16 relative noise
+    (the operand precision of the bf16x3 tensor-core path): the GPU error must stay within a small multiple of the
+    gradient change that perturbation causes.  (The sparse-conv gradients themselves are checked tightly in
+    tests/test_gpu_conv.py and tests/test_gpu_conv_tc.py.)"""
+    import copy
     from openscene_b200 import me, minkunet
     from oracle import matching as omatch
     from oracle import me_cpu
-    c = synth.random_cloud(1500, 20, seed=8, batch=2)
+    c = synth.scene('tiny')
     f = torch.rand(len(c), 3, generator=torch.Generator().manual_seed(0))
     tgt = torch.randn(len(c), 64, generator=torch.Generator().manual_seed(1))
     m64 = synth.build_model('MinkUNet14A', 64, seed=0, ME=minkunet.oracle_me()).double().train()
-    m32 = synth.build_model('MinkUNet14A', 64, seed=0, ME=minkunet.oracle_me()).train()
+    mpt = copy.deepcopy(m64)
+    g = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        for n_, p_ in mpt.named_parameters():
+            if n_.endswith('kernel'):
+                p_.mul_(1 + 2.0 ** -16 * torch.randn(p_.shape, generator=g, dtype=torch.float64))
     mg = synth.build_model('MinkUNet14A', 64, seed=0).to(DEV).train()
     o64 = m64(me_cpu.SparseTensor(f.double(), torch.from_numpy(c)))
-    o32 = m32(me_cpu.SparseTensor(f, torch.from_numpy(c)))
+    opt = mpt(me_cpu.SparseTensor(f.double(), torch.from_numpy(c)))
     og = mg(me.SparseTensor(f.to(DEV), torch.from_numpy(c).to(DEV)))
-    assert rel_row_err(og.detach().cpu().numpy(), o64.detach().numpy()) < TOL
+    e_fwd = rel_row_err(og.detach().cpu().numpy(), o64.detach().numpy())
+    e_fwd_pert = rel_row_err(opt.detach().numpy(), o64.detach().numpy())
+    print('forward rel err: gpu', e_fwd, ' 2^-16-perturbed oracle', e_fwd_pert)
+    assert e_fwd < max(TOL, 8 * e_fwd_pert)
     l64 = omatch.distill_loss(o64, tgt.double())
-    l32 = omatch.distill_loss(o32, tgt)
+    lpt = omatch.distill_loss(opt, tgt.double())
     lg = (1 - torch.nn.CosineSimilarity()(og, tgt.to(DEV))).mean()
-    assert abs(l64.item() - lg.item()) < 1e-5
-    l64.backward(); l32.backward(); lg.backward()
+    assert abs(l64.item() - lg.item()) < max(1e-5, 8 * abs(l64.item() - lpt.item()))
+    l64.backward(); lpt.backward(); lg.backward()
     worst = 0.0
-    for (n, p64), (_, p32), (_, pg) in zip(m64.named_parameters(), m32.named_parameters(), mg.named_parameters()):
+    for (n, p64), (_, ppt), (_, pg) in zip(m64.named_parameters(), mpt.named_parameters(), mg.named_parameters()):
         a = p64.grad.numpy()
-        e_ref = np.abs(a - p32.grad.numpy().astype(np.float64)).max()
+        e_pert = np.abs(a - ppt.grad.numpy()).max()
         e_gpu = np.abs(a - pg.grad.cpu().numpy().astype(np.float64)).max()
         scale = np.abs(a).max()
-        worst = max(worst, e_gpu / scale)
-        # BatchNorm here is torch's own CUDA implementation (exactly what the reference stack runs: ME wraps
-        # nn.BatchNorm1d); its batch statistics over the few voxels of the coarse levels differ from the CPU ones by more
-        # than fp32 round-off, and that difference propagates into every gradient.  The sparse-conv gradients themselves
-        # are checked tightly (5e-5) in tests/test_gpu_conv.py::test_conv_backward_matches_oracle_autograd.
-        assert e_gpu <= max(8 * e_ref, 5e-2 * scale), (n, e_gpu, e_ref, scale)
-    print('worst relative gradient error vs fp64 oracle:', worst)
-    assert worst < 5e-2
+        worst = max(worst, e_gpu / (e_pert + 1e-4 * scale))
+        assert e_gpu <= 10 * e_pert + 1e-3 * scale, (n, e_gpu, e_pert, scale)
+    print('worst gpu / perturbation gradient-error ratio:', worst)
     # running statistics were updated identically
     assert torch.allclose(m64.bn0.bn.running_mean.float(), mg.bn0.bn.running_mean.cpu(), atol=1e-5)
 
