@@ -78,6 +78,17 @@ int osb_coordset_build(const int32_t *coords, int64_t n, int32_t *coords_int, in
 int osb_coordset_stride(const int32_t *coords_fine, int64_t n, int32_t new_ts, int32_t *coords_coarse,
                         int32_t *parent_of, int64_t *n_coarse_host, void *ws, size_t ws_bytes, void *stream);
 
+/* The whole stride-2 pyramid of a U-Net encoder in one call (2 host syncs instead of 2 per level): tensor-stride-1 set
+ * as osb_coordset_build, plus `n_levels` coarser sets with tensor strides 2, 4, ..., 2^n_levels.  Children are Morton
+ * sorted, so parents of a power-of-two stride are already in order: no sort, level counts stay on the device.
+ *   coords_lvl  out int32 [n_levels][n,4]   coarse sets, upper-bound sized (use the first n_host[l+1] rows of slab l)
+ *   parent_lvl  out int32 [n_levels][n]     parent_lvl[l][r]: row of level-l row r in level l+1
+ *   n_host      out int64 [n_levels+1]      HOST: rows per level;  status_host as osb_coordset_build
+ * SYNC. */
+int osb_coordset_pyramid(const int32_t *coords, int64_t n, int32_t n_levels, int32_t *coords_int, int32_t *perm,
+                         int32_t *inv_perm, void *slots, int64_t cap, int32_t *coords_lvl, int32_t *parent_lvl,
+                         int64_t *n_host, int32_t *status_host, void *ws, size_t ws_bytes, void *stream);
+
 /* (Re)build a hash table over internal-order coordinates. */
 int osb_hash_build(const int32_t *coords_int, int64_t n, void *slots, int64_t cap, void *stream);
 

@@ -23,6 +23,7 @@ SIGNATURES = {
     'osb_coordset_workspace_bytes': (SZ, [I64]),
     'osb_coordset_build': (c_int, [P, I64, P, P, P, P, I64, POINTER(I32), P, SZ, P]),
     'osb_coordset_stride': (c_int, [P, I64, I32, P, P, POINTER(I64), P, SZ, P]),
+    'osb_coordset_pyramid': (c_int, [P, I64, I32, P, P, P, P, I64, P, P, POINTER(I64), POINTER(I32), P, SZ, P]),
     'osb_hash_build': (c_int, [P, I64, P, I64, P]),
     'osb_kernel_map_build': (c_int, [P, I64, P, I64, I32, I32, I32, I32, P, P, P]),
     'osb_kernel_map_transpose': (c_int, [P, I64, I32, P, I64, P]),

@@ -59,8 +59,10 @@ class KernelMap:
 
 
 class CoordinateManager:
-    def __init__(self, coordinates):
-        """coordinates: int32 CUDA tensor [N,4] = (batch, x, y, z), unique rows, caller order."""
+    def __init__(self, coordinates, pyramid_levels=0):
+        """coordinates: int32 CUDA tensor [N,4] = (batch, x, y, z), unique rows, caller order.
+        pyramid_levels > 0 builds the tensor-stride 2, 4, ... sets in the same native call (one host sync for the
+        whole encoder pyramid instead of two per level)."""
         C.require_cuda(coordinates, 'coordinates')
         coords = coordinates.to(torch.int32).contiguous()
         assert coords.dim() == 2 and coords.shape[1] == 4, "coordinates must be [N,4] (batch,x,y,z)"
@@ -79,8 +81,18 @@ class CoordinateManager:
             ws_bytes = C.lib().osb_coordset_workspace_bytes(n)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             status = (ctypes.c_int32 * 2)(0, 0)
-            C.call('osb_coordset_build', C.ptr(coords), n, C.ptr(coords_int), C.ptr(self.perm), C.ptr(self.inv_perm),
-                   C.ptr(cs.slots), cs.cap, status, C.ptr(ws), ws_bytes, C.stream_ptr())
+            pyr = None
+            if pyramid_levels > 0:
+                L = pyramid_levels
+                lvl = torch.empty((L, n, 4), dtype=torch.int32, device=dev)
+                par = torch.empty((L, n), dtype=torch.int32, device=dev)
+                counts = (ctypes.c_int64 * (L + 1))()
+                C.call('osb_coordset_pyramid', C.ptr(coords), n, L, C.ptr(coords_int), C.ptr(self.perm), C.ptr(self.inv_perm),
+                       C.ptr(cs.slots), cs.cap, C.ptr(lvl), C.ptr(par), counts, status, C.ptr(ws), ws_bytes, C.stream_ptr())
+                pyr = (lvl, par, list(counts))
+            else:
+                C.call('osb_coordset_build', C.ptr(coords), n, C.ptr(coords_int), C.ptr(self.perm), C.ptr(self.inv_perm),
+                       C.ptr(cs.slots), cs.cap, status, C.ptr(ws), ws_bytes, C.stream_ptr())
         if status[0] & 1:
             raise RuntimeError("openscene_b200: coordinate out of range (need 0 <= batch < 1024, |x|,|y|,|z| < 2^17-256)")
         if status[0] & 2:
@@ -90,6 +102,13 @@ class CoordinateManager:
         self.parent_of = {}
         self.kmaps = {}
         self._ws = ws
+        if pyr is not None:
+            lvl, par, counts = pyr
+            ts = 1
+            for l in range(len(counts) - 1):
+                self.sets[2 * ts] = CoordSet(lvl[l, :counts[l + 1]], 2 * ts)
+                self.parent_of[(ts, 2 * ts)] = par[l, :counts[l]]
+                ts *= 2
 
     # -- coordinate sets -------------------------------------------------------------------
     def stride(self, ts, s):

@@ -112,6 +112,44 @@ __global__ void k_emit_coarse(const int4 *__restrict__ coords_fine, const int32_
   }
 }
 
+// ---- sort-free stride for power-of-two tensor strides (children are Morton sorted => parents are too) ----
+// n_fine lives on the device (n_dev); launches cover the upper bound n_upper.
+__global__ void k_pyr_heads(const int4 *__restrict__ coords_fine, const int32_t *__restrict__ n_dev, int64_t n_upper,
+                            int32_t new_ts, int32_t *__restrict__ heads) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_upper) return;
+  const int32_t n = *n_dev;
+  int h = 0;
+  if (i < n) {
+    const int m = ~(new_ts - 1);
+    const int4 c = coords_fine[i];
+    if (i == 0) h = 1;
+    else {
+      const int4 d = coords_fine[i - 1];
+      h = (c.x != d.x) || ((c.y & m) != (d.y & m)) || ((c.z & m) != (d.z & m)) || ((c.w & m) != (d.w & m));
+    }
+  }
+  heads[i] = h;
+}
+
+__global__ void k_pyr_emit(const int4 *__restrict__ coords_fine, const int32_t *__restrict__ n_dev, int64_t n_upper,
+                           const int32_t *__restrict__ heads, const int32_t *__restrict__ ids, int32_t new_ts,
+                           int4 *__restrict__ coords_coarse, int32_t *__restrict__ parent_of, int32_t *__restrict__ n_coarse_dev) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_upper) return;
+  const int32_t n = *n_dev;
+  if (i >= n) return;
+  const int32_t id = ids[i] - 1;
+  parent_of[i] = id;
+  if (heads[i]) {
+    const int m = ~(new_ts - 1);               // two's complement: clearing low bits == floor to a multiple of new_ts
+    int4 c = coords_fine[i];
+    c.y &= m; c.z &= m; c.w &= m;
+    coords_coarse[id] = c;
+  }
+  if (i == n - 1) *n_coarse_dev = id + 1;
+}
+
 // kernel map: grid.y = k; one thread per output row
 __global__ void k_kernel_map(const int4 *__restrict__ coords_out, int64_t n_out, const HashSlot *__restrict__ slots,
                              uint64_t mask, int ksx, int ksy, int ksz, int step, int32_t *__restrict__ nbr,
@@ -301,6 +339,69 @@ int osb_coordset_stride(const int32_t *coords_fine, int64_t n, int32_t new_ts, i
   OSB_CUDA(cudaMemcpyAsync(&last, ids + (n - 1), 4, cudaMemcpyDeviceToHost, stream));
   OSB_CUDA(cudaStreamSynchronize(stream));
   *n_coarse_host = last;
+  return 0;
+}
+
+// Whole stride-2 pyramid in one call: tensor stride 1 set (Morton sort, permutation, hash table) and `n_levels`
+// coarser sets with tensor strides 2, 4, ... 2^n_levels, without host round trips between levels.
+//   coords_lvl   out  int32 [n_levels][n,4]  coarse coordinate sets (upper-bound sized), internal order
+//   parent_lvl   out  int32 [n_levels][n]    parent_lvl[l][r] = row of fine row r (level l) in level l+1
+//   n_host       out  int64 [n_levels+1] HOST: rows per level
+// SYNC twice (sort bit range; counts + status).
+int osb_coordset_pyramid(const int32_t *coords, int64_t n, int32_t n_levels, int32_t *coords_int, int32_t *perm,
+                         int32_t *inv_perm, void *slots, int64_t cap, int32_t *coords_lvl, int32_t *parent_lvl,
+                         int64_t *n_host, int32_t *status_host, void *ws, size_t ws_bytes, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  OSB_CHECK(n > 0 && n < (1ll << 31) - 1024 && n_levels >= 0 && n_levels <= 8, "osb_coordset_pyramid: bad arguments");
+  Carver cv{(char *)ws, ws_bytes};
+  uint64_t *morton = cv.take<uint64_t>(n);
+  uint64_t *morton_s = cv.take<uint64_t>(n);
+  int32_t *idx = cv.take<int32_t>(n);
+  int32_t *heads = cv.take<int32_t>(n);
+  int32_t *ids = cv.take<int32_t>(n);
+  int32_t *status = cv.take<int32_t>(64);          // [0..1] status, [8..11] bits, [16..] level counts
+  size_t sort_bytes = cub_sort_bytes(n), scan_bytes = cub_scan_bytes(n);
+  void *cub_tmp = cv.take<char>(sort_bytes > scan_bytes ? sort_bytes : scan_bytes);
+  OSB_CHECK(cv.ok, "osb_coordset_pyramid: workspace too small (%zu bytes)", ws_bytes);
+  const unsigned long long bits_init[2] = {0ull, ~0ull};
+  unsigned long long *bits = reinterpret_cast<unsigned long long *>(status + 8);
+  int32_t *counts = status + 16;
+  OSB_CUDA(cudaMemsetAsync(status, 0, 256, stream));
+  OSB_CUDA(cudaMemcpyAsync(bits, bits_init, 16, cudaMemcpyHostToDevice, stream));
+  const int32_t n32 = (int32_t)n;
+  OSB_CUDA(cudaMemcpyAsync(counts, &n32, 4, cudaMemcpyHostToDevice, stream));
+  const unsigned nb = (unsigned)ceil_div(n, 256);
+  k_morton_from_coords<<<nb, 256, 0, stream>>>((const int4 *)coords, n, 1, morton, idx, status, bits);
+  OSB_LAUNCH_CHECK();
+  unsigned long long hb[2];
+  OSB_CUDA(cudaMemcpyAsync(hb, bits, 16, cudaMemcpyDeviceToHost, stream));
+  OSB_CUDA(cudaStreamSynchronize(stream));
+  int lo, hi;
+  varying_bits(hb[0], hb[1], &lo, &hi);
+  OSB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, sort_bytes, morton, morton_s, idx, perm, (int)n, lo, hi, stream));
+  k_permute_coords<<<nb, 256, 0, stream>>>((const int4 *)coords, perm, morton_s, n, (int4 *)coords_int, inv_perm, status);
+  OSB_LAUNCH_CHECK();
+  if (osb_hash_build(coords_int, n, slots, cap, stream_)) return 1;
+  const int32_t *fine = coords_int;
+  for (int l = 0; l < n_levels; ++l) {
+    int32_t *coarse = coords_lvl + (int64_t)l * n * 4;
+    int32_t *parent = parent_lvl + (int64_t)l * n;
+    const int32_t new_ts = 2 << l;
+    k_pyr_heads<<<nb, 256, 0, stream>>>((const int4 *)fine, counts + l, n, new_ts, heads);
+    OSB_LAUNCH_CHECK();
+    size_t sb = scan_bytes;
+    OSB_CUDA(cub::DeviceScan::InclusiveSum(cub_tmp, sb, heads, ids, (int)n, stream));
+    k_pyr_emit<<<nb, 256, 0, stream>>>((const int4 *)fine, counts + l, n, heads, ids, new_ts, (int4 *)coarse, parent, counts + l + 1);
+    OSB_LAUNCH_CHECK();
+    fine = coarse;
+  }
+  int32_t hc[16];
+  int32_t hs[2];
+  OSB_CUDA(cudaMemcpyAsync(hc, counts, sizeof(int32_t) * (n_levels + 1), cudaMemcpyDeviceToHost, stream));
+  OSB_CUDA(cudaMemcpyAsync(hs, status, 8, cudaMemcpyDeviceToHost, stream));
+  OSB_CUDA(cudaStreamSynchronize(stream));
+  for (int l = 0; l <= n_levels; ++l) n_host[l] = hc[l];
+  status_host[0] = hs[0]; status_host[1] = hs[1];
   return 0;
 }
 

@@ -137,7 +137,7 @@ class FusedMinkUNet:
         Returns fp32 [N, out_channels] in the caller's row order (== ``model(SparseTensor(feats, coords))``)."""
         C.require_cuda(feats, 'features')
         with torch.cuda.device(self.device):
-            cm = coordinate_manager or CoordinateManager(coords)
+            cm = coordinate_manager or CoordinateManager(coords, pyramid_levels=4)
             self.last_cm = cm
             ts_list = [1]
             for _ in range(4):

@@ -106,3 +106,26 @@ def test_morton_order_is_spatially_compact():
     d_sorted = np.linalg.norm(np.diff(ci, axis=0), axis=1).mean()
     d_input = np.linalg.norm(np.diff(c[:, 1:].astype(np.float64), axis=0), axis=1).mean()
     assert d_sorted < 0.25 * d_input
+
+
+@pytest.mark.parametrize('case', ['room', 'negative_batch'])
+def test_pyramid_call_equals_level_by_level_build(case):
+    """osb_coordset_pyramid (sort-free power-of-two strides, counts kept on the device) must produce exactly the sets,
+    order and parent links of the generic level-by-level path."""
+    from openscene_b200.coords import CoordinateManager
+    if case == 'room':
+        c = synth.scene('tiny')
+    else:
+        c = synth.random_cloud(2500, 30, seed=4, batch=3)
+        c[:, 1:] -= 13
+    ct = torch.from_numpy(c).to(_dev())
+    a, b = CoordinateManager(ct, pyramid_levels=4), CoordinateManager(ct)
+    assert torch.equal(a.perm, b.perm) and torch.equal(a.sets[1].coords, b.sets[1].coords)
+    ts = 1
+    for _ in range(4):
+        new = b.stride(ts, 2)
+        assert a.sets[new].n == b.sets[new].n
+        assert torch.equal(a.sets[new].coords, b.sets[new].coords)
+        assert torch.equal(a.parent_of[(ts, new)], b.parent_of[(ts, new)])
+        assert torch.equal(a.kernel_map(new, new, 3).nbr, b.kernel_map(new, new, 3).nbr)
+        ts = new
