@@ -76,6 +76,7 @@ class FusedMinkUNet:
         self._ws = None
         import os
         self.use_pdl = os.environ.get('OSB_PDL', '1') != '0'
+        self.use_pyramid = os.environ.get('OSB_PYRAMID', '1') != '0'
 
     @staticmethod
     def _blocks(seq):
@@ -137,7 +138,7 @@ class FusedMinkUNet:
         Returns fp32 [N, out_channels] in the caller's row order (== ``model(SparseTensor(feats, coords))``)."""
         C.require_cuda(feats, 'features')
         with torch.cuda.device(self.device):
-            cm = coordinate_manager or CoordinateManager(coords, pyramid_levels=4)
+            cm = coordinate_manager or CoordinateManager(coords, pyramid_levels=4 if self.use_pyramid else 0)
             self.last_cm = cm
             ts_list = [1]
             for _ in range(4):

@@ -20,11 +20,13 @@ for _ in range(3):
     matching._scores(eng(coords, feats), None, text, normalize=True)
 torch.cuda.synchronize()
 R = 20
-t_cm = t_fw = t_mt = 0.0
+PYR = int(os.environ.get('PYR', '4'))
+t_cm = t_fw = t_mt = t_b = 0.0
 t0 = time.perf_counter()
 for _ in range(R):
     a = time.perf_counter()
-    cm = CoordinateManager(coords)
+    cm = CoordinateManager(coords, pyramid_levels=PYR)
+    torch.cuda.synchronize(); a1 = time.perf_counter(); t_b += a1 - a
     ts = 1
     for _ in range(4):
         ts = cm.stride(ts, 2)
@@ -40,5 +42,6 @@ for _ in range(R):
     t_cm += b - a; t_fw += c - b; t_mt += d - c
 torch.cuda.synchronize()
 tot = time.perf_counter() - t0
+print(f'PYR={PYR} build+sync {1e3 * t_b / R:.2f} ms;', end=' ')
 print(f'per step: wall {1e3 * tot / R:.2f} ms | host: coordinate phase (incl. its syncs) {1e3 * t_cm / R:.2f} ms, '
       f'conv-chain enqueue {1e3 * t_fw / R:.2f} ms, match enqueue {1e3 * t_mt / R:.3f} ms')
