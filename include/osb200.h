@@ -181,6 +181,12 @@ int osb_match_ensemble(const float *feat3d, const void *feat2d_f16, int64_t n_vo
                        const void *text_f16, int32_t k_text, void *scores_f16, int64_t *label, void *feat_out_f16,
                        void *stream);
 
+/* Optional folded head (engine.forward_scores): rows z = [x L | x U] (fp32, row pitch ld floats) from one 1x1x1
+ * convolution with the weights [L | U], W W^T = L L^T, U = W T^T  ->  score_k = fp16((x.U_k) / (|x L| + 1e-5)),
+ * label = first argmax.  Same cosine scores as run/evaluate.py:305-310 without materialising the 768-d features. */
+int osb_folded_head_finish(const float *z, int64_t n, int32_t ld, int32_t c_norm, int32_t k_text, void *scores_f16,
+                           int64_t *label, float *smax, void *stream);
+
 /* ------------------------------------------------------------- voxeliser
  * coords (fp32 or fp64 [n,3]) -> c = floor([p,1] . M^T[:, :3]) with M the HOST 4x4 row-major fp64 matrix,
  * c -= min(c), FNV-64 key (multiply-then-xor over uint64 words), unique by ascending key keeping the

@@ -18,6 +18,7 @@ k_conv_stem(const float *__restrict__ in, int cin, const int4 *__restrict__ coor
             float *__restrict__ out_f32) {
   extern __shared__ float4 s_w4[];                     // [K][32]: (W[k][0][n], W[k][1][n], W[k][2][n], 0)
   __shared__ float4 s_hit[STEM_WARPS][32];
+  __shared__ unsigned long long s_dk[352];             // packed key delta of every offset (no div/mod in the probe loop)
   const int K = ks * ks * ks;
   for (int e = threadIdx.x; e < K * 32; e += blockDim.x) {
     const int k = e >> 5, nn = e & 31;
@@ -29,24 +30,26 @@ k_conv_stem(const float *__restrict__ in, int cin, const int4 *__restrict__ coor
     }
     s_w4[e] = v;
   }
+  const int half = ks / 2;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const int ix = k % ks, iy = (k / ks) % ks, iz = k / (ks * ks);
+    const int dx = ((ks & 1) ? ix - half : ix) * step, dy = ((ks & 1) ? iy - half : iy) * step,
+              dz = ((ks & 1) ? iz - half : iz) * step;
+    s_dk[k] = pack_delta(dx, dy, dz);
+  }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int half = ks / 2;
   const float sc = (scale && lane < cout) ? __ldg(scale + lane) : 1.f;
   const float sh = (shift && lane < cout) ? __ldg(shift + lane) : 0.f;
   const int64_t warps_total = (int64_t)gridDim.x * STEM_WARPS;
   for (int64_t o = (int64_t)blockIdx.x * STEM_WARPS + warp; o < n; o += warps_total) {
     const int4 c = __ldg(coords + o);
+    const uint64_t base = pack_key(c.x, c.y, c.z, c.w);
     float acc = 0.f;
     for (int kb = 0; kb < K; kb += 32) {
       const int k = kb + lane;
       int row = -1;
-      if (k < K) {
-        const int ix = k % ks, iy = (k / ks) % ks, iz = k / (ks * ks);
-        const int dx = ((ks & 1) ? ix - half : ix) * step, dy = ((ks & 1) ? iy - half : iy) * step,
-                  dz = ((ks & 1) ? iz - half : iz) * step;
-        row = hash_lookup(slots, mask, pack_key(c.x, c.y + dx, c.z + dy, c.w + dz));
-      }
+      if (k < K) row = hash_lookup(slots, mask, base + s_dk[k]);   // neighbour key = one 64-bit add
       float4 h = make_float4(0.f, 0.f, 0.f, __int_as_float(k));
       if (row >= 0) {
         const float *xp = in + (int64_t)row * cin;

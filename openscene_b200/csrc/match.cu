@@ -202,3 +202,54 @@ int osb_match_ensemble(const float *feat3d, const void *feat2d_f16, int64_t n_vo
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// Folded head (optional fast path, openscene_b200/engine.py: forward_scores): the final 1x1x1 convolution
+// f = x W (96 -> 768) and the cosine product with the text matrix T are re-associated,
+//     f . t_k = x . (W t_k) = x . U_k,      |f|^2 = x (W W^T) x^T = |x L|^2   (W W^T = L L^T, Cholesky),
+// so one 96 -> (96 + K) convolution produces z = [x L | x U] and this kernel finishes a row:
+//     score_k = fp16( (x.U_k) / (|x L| + 1e-5) ),  label = argmax_k.
+namespace osb {
+__global__ void k_folded_head_finish(const float *__restrict__ z, int64_t n, int ld, int c_norm, int k_text,
+                                     __half *__restrict__ scores, int64_t *__restrict__ label, float *__restrict__ smax) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t p = warp; p < n; p += nwarps) {
+    const float *row = z + p * ld;
+    float ss = 0.f;
+    for (int c = lane; c < c_norm; c += 32) { const float v = __ldg(row + c); ss = fmaf(v, v, ss); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float d = sqrtf(ss) + 1e-5f;
+    float best = -INFINITY;
+    int best_k = 0x7fffffff;
+    for (int k = lane; k < k_text; k += 32) {
+      const __half h = __float2half_rn(__ldg(row + c_norm + k) / d);
+      if (scores) scores[p * k_text + k] = h;
+      const float s = __half2float(h);
+      if (s > best) { best = s; best_k = k; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
+      if (ob > best || (ob == best && ok < best_k)) { best = ob; best_k = ok; }
+    }
+    if (lane == 0) {
+      if (label) label[p] = best_k;
+      if (smax) smax[p] = best;
+    }
+  }
+}
+}  // namespace osb
+
+extern "C" int osb_folded_head_finish(const float *z, int64_t n, int32_t ld, int32_t c_norm, int32_t k_text, void *scores_f16,
+                                      int64_t *label, float *smax, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  OSB_CHECK(n > 0 && c_norm > 0 && k_text > 0 && ld >= c_norm + k_text, "osb_folded_head_finish: bad shape");
+  const unsigned grid = (unsigned)std::min<int64_t>(osb::ceil_div(n, 8), 148 * 8);
+  osb::k_folded_head_finish<<<grid, 256, 0, stream>>>(z, n, ld, c_norm, k_text, (__half *)scores_f16, label, smax);
+  OSB_LAUNCH_CHECK();
+  return 0;
+}

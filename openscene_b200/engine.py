@@ -133,7 +133,7 @@ class FusedMinkUNet:
         return x[0]
 
     @torch.no_grad()
-    def forward(self, coords, feats, coordinate_manager=None):
+    def forward(self, coords, feats, coordinate_manager=None, head=None):
         """coords int32 [N,4] (batch,x,y,z), feats fp32 [N,cin], both CUDA, caller order.
         Returns fp32 [N, out_channels] in the caller's row order (== ``model(SparseTensor(feats, coords))``)."""
         C.require_cuda(feats, 'features')
@@ -180,6 +180,10 @@ class FusedMinkUNet:
                 l = 3 - j                                   # output level of this transposed conv
                 y = self._conv(uconv, [cur], up_nbr[l].data_ptr(), n[l])
                 cur = self._stage(blocks, [(y, uconv.cout, n[l]), skips[l]], nbr3_a[l], n[l])
+            if head is not None:                           # folded head: 96 -> (96 + K) conv, rows straight in caller order
+                z = torch.empty((n[0], head.cout), dtype=torch.float32, device=self.device)
+                self._conv(head, [cur], 0, n[0], relu=0, out_f32_a=z.data_ptr(), row_map_a=cm.perm.data_ptr())
+                return z
             fin = self.final
             out = torch.empty((n[0], fin.cout), dtype=torch.float32, device=self.device)
             if fin.wpack is not None:
@@ -195,6 +199,42 @@ class FusedMinkUNet:
             return ext
 
     __call__ = forward
+
+    # ---------------------------------------------------------------------------------------
+    def fold_head(self, text_features):
+        """Pre-compute the folded head for a set of unit-norm text embeddings [K, C_out]:
+        W W^T = L L^T (Cholesky, fp64) and U = W T^T, packed as one 1x1x1 convolution 96 -> (96 + K)."""
+        W = self.final.w3[0].double()                                    # [cin, cout]
+        T = text_features.to(W.device).double()                          # [K, cout]
+        G = W @ W.t()
+        G = G + 1e-12 * torch.eye(G.shape[0], device=G.device, dtype=G.dtype) * G.diagonal().mean()
+        L = torch.linalg.cholesky(G)                                     # x G x^T = |x L|^2
+        U = W @ T.t()
+        cin, k = W.shape[0], T.shape[0]
+        cout = ((cin + k + 31) // 32) * 32
+        w = torch.zeros((1, cin, cout), dtype=torch.float32, device=W.device)
+        w[0, :, :cin] = L.float()
+        w[0, :, cin:cin + k] = U.float()
+        cv = _Conv.__new__(_Conv)
+        cv.K, cv.cin, cv.cout, cv.ks, cv.stride, cv.transpose = 1, cin, cout, 1, 1, False
+        cv.w3, cv.wpack = w, tc.pack_weights(w)
+        cv.scale = cv.shift = None
+        cv.wpack_a, cv.scale_a, cv.shift_a = cv.wpack.data_ptr(), 0, 0
+        return (cv, cin, k)
+
+    @torch.no_grad()
+    def forward_scores(self, coords, feats, folded, want_scores=True):
+        """Cosine scores / labels of every voxel against the folded text set (``fold_head``), equal to
+        ``match(normalize(forward(coords, feats)), text)`` up to rounding, without the 768-d features.
+        Returns (scores fp16 [N,K] or None, label int64 [N], smax fp32 [N]) in the caller's row order."""
+        cv, cin, k = folded
+        z = self.forward(coords, feats, head=cv)
+        n = z.shape[0]
+        scores = torch.empty((n, k), dtype=torch.float16, device=self.device) if want_scores else None
+        label = torch.empty(n, dtype=torch.int64, device=self.device)
+        smax = torch.empty(n, dtype=torch.float32, device=self.device)
+        C.call('osb_folded_head_finish', C.ptr(z), n, cv.cout, cin, k, C.ptr(scores), C.ptr(label), C.ptr(smax), C.stream_ptr())
+        return scores, label, smax
 
     def conv_census(self, cm):
         """Per-convolution (name, pairs, cin, cout, n_in, n_out) of the last forward: algorithmic flops / bytes

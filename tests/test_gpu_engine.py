@@ -43,3 +43,19 @@ def test_engine_refuses_train_mode():
     model = synth.build_model('MinkUNet14A', 64, seed=0).to(DEV).train()
     with pytest.raises(RuntimeError, match='eval'):
         engine.FusedMinkUNet(model)
+
+
+def test_folded_head_scores_match_materialised_path():
+    """engine.forward_scores (final conv folded with the text matrix) against normalise + match on the 768-d features."""
+    from openscene_b200 import engine, matching
+    c = torch.from_numpy(synth.scene('tiny')).to(DEV)
+    f = torch.rand(c.shape[0], 3, device=DEV, generator=torch.Generator(device=DEV).manual_seed(1))
+    model = synth.build_model('MinkUNet18A', 768, seed=0).eval().to(DEV)
+    eng = engine.FusedMinkUNet(model)
+    text = torch.from_numpy(synth.text_embeddings(20)).to(DEV)
+    s_ref, l_ref, m_ref = matching._scores(eng(c, f), None, text, normalize=True, want_smax=True)
+    s, l, m = eng.forward_scores(c, f, eng.fold_head(text.float()))
+    assert s.shape == s_ref.shape and s.dtype == torch.float16
+    assert (s.float() - s_ref.float()).abs().max() < 2e-3          # both are fp16 roundings of the same cosine
+    assert (l == l_ref).float().mean() > 0.99
+    assert torch.equal(l, s.float().max(1)[1])
