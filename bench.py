@@ -31,7 +31,7 @@ def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=50)
-    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='osb200', choices=['osb200', 'reference'])
     ap.add_argument('--workload', default='config2_200k')
     ap.add_argument('--arch', default='MinkUNet34C')
@@ -221,8 +221,13 @@ def main():
         buf.copy_(label, non_blocking=True)
         return buf
 
-    def timed(fn, k, sampler=None):
+    step_stats = {}
+
+    def timed(fn, k, sampler=None, tag=None):
+        import gc
         evs = []
+        gc.collect()
+        gc.disable()                                                 # no collector pauses between enqueues
         for i in range(k):
             flush.zero_()                                            # L2 flush, outside the timed events
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -232,7 +237,11 @@ def main():
                 sampler.sample()                                     # GPU still busy with this step; outside its event pair
                                                                      # (each NVML query stalls the CPU for ms: keep them few)
         torch.cuda.synchronize()
-        return sum(a.elapsed_time(b) for a, b in evs)
+        gc.enable()
+        ts = sorted(a.elapsed_time(b) for a, b in evs)
+        if tag:
+            step_stats[tag] = {'min': ts[0], 'median': ts[len(ts) // 2], 'max': ts[-1]}
+        return sum(ts)
 
     def barrier():
         if world > 1:
@@ -244,14 +253,17 @@ def main():
         step_device()
     barrier()
     l0 = _cabi.lib().osb_launch_count()
-    ms_dev = timed(step_device, args.steps, sampler)
+    if sampler:
+        sampler.sample()                                       # first NVML calls cost milliseconds: pay them before the timed region
+        sampler.sm.clear(); sampler.power.clear(); sampler.reasons.clear()
+    ms_dev = timed(step_device, args.steps, sampler, tag='device')
     launches = _cabi.lib().osb_launch_count() - l0
     barrier()
     clocks = sampler.stop() if sampler else None
     for _ in range(2):
         step_e2e()
     barrier()
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e = timed(step_e2e, args.steps, tag='e2e')
     barrier()
 
     # ---- optional re-associated head (not the headline: the 768-d features are not materialised) -----
@@ -318,7 +330,7 @@ def main():
                        'points': 'stride-1 voxels fed to SparseTensor'},
             'e2e': {'value': total_vox * args.steps / (t_e2e / 1e3), 'unit': 'voxels/s', 'ms_per_step': t_e2e / args.steps,
                     'h2d_bytes_per_step': int(coords_host.numel() * 4 + feats_host.numel() * 4), 'd2h_bytes_per_step': int(n0 * 8)},
-            'gpu_launches': int(launches), 'clocks': clocks,
+            'gpu_launches': int(launches), 'clocks': clocks, 'step_ms_stats': step_stats,
         }
         if ms_folded is not None:
             line['extra'] = {'folded_head_ms_per_step': ms_folded,
