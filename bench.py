@@ -69,6 +69,7 @@ class ClockSampler:
             self.err = str(e)
 
     def sample(self):
+        """SM clock + clock-event reasons only: the power query stalls the GPU for tens of milliseconds."""
         if not self.ok:
             return
         nv = self.nv
@@ -78,7 +79,6 @@ class ClockSampler:
             for name, bit in self.REASONS.items():
                 if r & bit:
                     self.reasons.add(name)
-            self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1e3)
         except Exception:                 # noqa: BLE001
             pass
 
