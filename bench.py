@@ -234,8 +234,12 @@ def main():
             a.record(); fn(); b.record()
             evs.append((a, b))
             if sampler is not None and i in (k // 4, k // 2, (3 * k) // 4):
-                sampler.sample()                                     # GPU still busy with this step; outside its event pair
-                                                                     # (each NVML query stalls the CPU for ms: keep them few)
+                # An NVML query issued while kernels are in flight stalls the GPU for 20-60 ms (measured: per-step max of
+                # 34-67 ms against a 4.6 ms median), and that lands inside the event pair of the step being executed.
+                # So: drain the stream, query right away (the clock / throttle state of a GPU that was busy microseconds
+                # ago), continue.  The drain is outside every event pair.
+                torch.cuda.synchronize()
+                sampler.sample()
         torch.cuda.synchronize()
         gc.enable()
         ts = sorted(a.elapsed_time(b) for a, b in evs)
