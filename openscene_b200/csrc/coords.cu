@@ -6,11 +6,11 @@
 // consecutive rows is a compact surface patch whose 27-neighbourhoods overlap (gather locality).
 #include "common.cuh"
 
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
+#include "sortscan.cuh"
 
 #include <stdarg.h>
 #include <string.h>
+#include <algorithm>
 
 namespace osb {
 
@@ -205,12 +205,8 @@ struct Carver {
   }
 };
 
-static size_t cub_sort_bytes(int64_t n) {
-  size_t b = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, b, (const uint64_t *)nullptr, (uint64_t *)nullptr, (const int32_t *)nullptr,
-                                  (int32_t *)nullptr, (int)n, 0, 64, (cudaStream_t)0);
-  return b;
-}
+static size_t cub_sort_bytes(int64_t n) { return radix_sort_ws_bytes(n); }
+
 // digit range [lo, hi) of the bits in which the keys differ (OR & ~AND), rounded to the 8-bit radix passes
 static void varying_bits(unsigned long long k_or, unsigned long long k_and, int *lo, int *hi) {
   const unsigned long long diff = k_or & ~k_and;
@@ -221,10 +217,19 @@ static void varying_bits(unsigned long long k_or, unsigned long long k_and, int 
   *lo = l; *hi = h;
 }
 
-static size_t cub_scan_bytes(int64_t n) {
-  size_t b = 0;
-  cub::DeviceScan::InclusiveSum(nullptr, b, (const int32_t *)nullptr, (int32_t *)nullptr, (int)n, (cudaStream_t)0);
-  return b;
+static size_t cub_scan_bytes(int64_t n) { return scan_ws_bytes(n); }
+
+// Sort (key, index) pairs over bits [lo, hi) such that the sorted keys land in *keys_sorted and the permutation in `perm`.
+// `k0` holds the keys (clobbered), `k1` / `v_tmp` are scratch.
+static int sort_to(uint64_t *k0, uint64_t *k1, int32_t *v_tmp, int32_t *perm, int64_t n, int lo, int hi, void *ws,
+                   cudaStream_t stream, uint64_t **keys_sorted) {
+  const int passes = std::max(1, (hi - lo + 7) / 8);
+  // the result of an odd number of passes lands in the 'b' buffers
+  int32_t *va = (passes & 1) ? v_tmp : perm, *vb = (passes & 1) ? perm : v_tmp;
+  const int where = radix_sort_pairs(k0, va, k1, vb, nullptr, n, lo, hi, ws, stream);
+  if (where < 0) return 1;
+  *keys_sorted = where ? k1 : k0;
+  return 0;
 }
 
 }  // namespace osb
@@ -292,8 +297,9 @@ int osb_coordset_build(const int32_t *coords, int64_t n, int32_t *coords_int, in
   OSB_CUDA(cudaStreamSynchronize(stream));
   int lo, hi;
   varying_bits(hb[0], hb[1], &lo, &hi);
-  OSB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, sort_bytes, morton, morton_s, idx, perm, (int)n, lo, hi, stream));
-  k_permute_coords<<<nb, 256, 0, stream>>>((const int4 *)coords, perm, morton_s, n, (int4 *)coords_int, inv_perm, status);
+  uint64_t *sorted_keys = nullptr;
+  OSB_CHECK(sort_to(morton, morton_s, idx, perm, n, lo, hi, cub_tmp, stream, &sorted_keys) == 0, "osb_coordset_build: sort failed");
+  k_permute_coords<<<nb, 256, 0, stream>>>((const int4 *)coords, perm, sorted_keys, n, (int4 *)coords_int, inv_perm, status);
   OSB_LAUNCH_CHECK();
   if (osb_hash_build(coords_int, n, slots, cap, stream_)) return 1;
   OSB_CUDA(cudaMemcpyAsync(status_host, status, 8, cudaMemcpyDeviceToHost, stream));
@@ -328,10 +334,11 @@ int osb_coordset_stride(const int32_t *coords_fine, int64_t n, int32_t new_ts, i
   OSB_CUDA(cudaStreamSynchronize(stream));
   int lo, hi;
   varying_bits(hb[0], hb[1], &lo, &hi);
-  OSB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, sort_bytes, key, key_s, idx, order, (int)n, lo, hi, stream));
-  k_run_heads<<<nb, 256, 0, stream>>>(key_s, n, heads);
+  uint64_t *sorted_keys = nullptr;
+  OSB_CHECK(sort_to(key, key_s, idx, order, n, lo, hi, cub_tmp, stream, &sorted_keys) == 0, "osb_coordset_stride: sort failed");
+  k_run_heads<<<nb, 256, 0, stream>>>(sorted_keys, n, heads);
   OSB_LAUNCH_CHECK();
-  OSB_CUDA(cub::DeviceScan::InclusiveSum(cub_tmp, scan_bytes, heads, ids, (int)n, stream));
+  OSB_CHECK(inclusive_scan_i32(heads, ids, n, cub_tmp, stream) == 0, "osb_coordset_stride: scan failed");
   k_emit_coarse<<<nb, 256, 0, stream>>>((const int4 *)coords_fine, order, heads, ids, n, new_ts, (int4 *)coords_coarse,
                                         parent_of);
   OSB_LAUNCH_CHECK();
@@ -378,8 +385,9 @@ int osb_coordset_pyramid(const int32_t *coords, int64_t n, int32_t n_levels, int
   OSB_CUDA(cudaStreamSynchronize(stream));
   int lo, hi;
   varying_bits(hb[0], hb[1], &lo, &hi);
-  OSB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, sort_bytes, morton, morton_s, idx, perm, (int)n, lo, hi, stream));
-  k_permute_coords<<<nb, 256, 0, stream>>>((const int4 *)coords, perm, morton_s, n, (int4 *)coords_int, inv_perm, status);
+  uint64_t *sorted_keys = nullptr;
+  OSB_CHECK(sort_to(morton, morton_s, idx, perm, n, lo, hi, cub_tmp, stream, &sorted_keys) == 0, "osb_coordset_pyramid: sort failed");
+  k_permute_coords<<<nb, 256, 0, stream>>>((const int4 *)coords, perm, sorted_keys, n, (int4 *)coords_int, inv_perm, status);
   OSB_LAUNCH_CHECK();
   if (osb_hash_build(coords_int, n, slots, cap, stream_)) return 1;
   const int32_t *fine = coords_int;
@@ -389,8 +397,7 @@ int osb_coordset_pyramid(const int32_t *coords, int64_t n, int32_t n_levels, int
     const int32_t new_ts = 2 << l;
     k_pyr_heads<<<nb, 256, 0, stream>>>((const int4 *)fine, counts + l, n, new_ts, heads);
     OSB_LAUNCH_CHECK();
-    size_t sb = scan_bytes;
-    OSB_CUDA(cub::DeviceScan::InclusiveSum(cub_tmp, sb, heads, ids, (int)n, stream));
+    OSB_CHECK(inclusive_scan_i32(heads, ids, n, cub_tmp, stream) == 0, "osb_coordset_pyramid: scan failed");
     k_pyr_emit<<<nb, 256, 0, stream>>>((const int4 *)fine, counts + l, n, heads, ids, new_ts, (int4 *)coarse, parent, counts + l + 1);
     OSB_LAUNCH_CHECK();
     fine = coarse;

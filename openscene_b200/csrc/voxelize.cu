@@ -3,8 +3,8 @@
 // dataset/voxelizer.py:116-130 + dataset/voxelization_utils.py:9-22,107-131 (np.unique semantics).
 #include "common.cuh"
 
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
+#include "sortscan.cuh"
+#include <algorithm>
 
 namespace osb {
 
@@ -89,14 +89,7 @@ struct VCarver {
   }
 };
 
-static size_t vox_sort_bytes(int64_t n) {
-  size_t b = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, b, (const uint64_t *)nullptr, (uint64_t *)nullptr, (const int32_t *)nullptr,
-                                  (int32_t *)nullptr, (int)n, 0, 64, (cudaStream_t)0);
-  size_t c = 0;
-  cub::DeviceScan::InclusiveSum(nullptr, c, (const int32_t *)nullptr, (int32_t *)nullptr, (int)n, (cudaStream_t)0);
-  return b > c ? b : c;
-}
+static size_t vox_sort_bytes(int64_t n) { return std::max(radix_sort_ws_bytes(n), scan_ws_bytes(n)); }
 
 }  // namespace osb
 
@@ -139,13 +132,15 @@ int osb_voxelize(const void *coords, int32_t coords_is_f64, int64_t n, const dou
   OSB_LAUNCH_CHECK();
   k_vox_keys<<<nb, 256, 0, stream>>>(cint, cmin, n, key, idx, c32);
   OSB_LAUNCH_CHECK();
-  size_t tb = tmp_bytes;
-  OSB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, key, key_s, idx, idx_s, (int)n, 0, 64, stream));
-  k_vox_heads<<<nb, 256, 0, stream>>>(key_s, n, heads);
+  // stable LSD radix sort over all 64 key bits (8 passes: an even count, so the result is back in the 'a' buffers)
+  const int where = radix_sort_pairs(key, idx, key_s, idx_s, nullptr, n, 0, 64, tmp, stream);
+  OSB_CHECK(where >= 0, "osb_voxelize: sort failed");
+  const uint64_t *ks = where ? key_s : key;
+  const int32_t *is = where ? idx_s : idx;
+  k_vox_heads<<<nb, 256, 0, stream>>>(ks, n, heads);
   OSB_LAUNCH_CHECK();
-  tb = tmp_bytes;
-  OSB_CUDA(cub::DeviceScan::InclusiveSum(tmp, tb, heads, ids, (int)n, stream));
-  k_vox_emit<<<nb, 256, 0, stream>>>(idx_s, heads, ids, c32, n, coords_vox, inds, inds_reverse);
+  OSB_CHECK(inclusive_scan_i32(heads, ids, n, tmp, stream) == 0, "osb_voxelize: scan failed");
+  k_vox_emit<<<nb, 256, 0, stream>>>(is, heads, ids, c32, n, coords_vox, inds, inds_reverse);
   OSB_LAUNCH_CHECK();
   int32_t last = 0;
   long long hmin[4];

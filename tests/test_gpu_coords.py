@@ -129,3 +129,27 @@ def test_pyramid_call_equals_level_by_level_build(case):
         assert torch.equal(a.parent_of[(ts, new)], b.parent_of[(ts, new)])
         assert torch.equal(a.kernel_map(new, new, 3).nbr, b.kernel_map(new, new, 3).nbr)
         ts = new
+
+
+def test_hand_written_sort_handles_many_tiles_and_wide_keys():
+    """The LSD radix sort (csrc/sortscan.cuh) behind the Morton ordering: > 100 tiles, three batches, coordinates spread
+    over 15 bits per axis (6 radix passes).  The internal order must be the stable Morton order."""
+    from openscene_b200.coords import CoordinateManager
+    rng = np.random.RandomState(0)
+    c = np.unique(np.concatenate([rng.randint(0, 3, (300_000, 1)), rng.randint(-16000, 16000, (300_000, 3))], 1), axis=0)
+    c = c[rng.permutation(len(c))].astype(np.int32)
+    cm = CoordinateManager(torch.from_numpy(c).to(_dev()), pyramid_levels=2)
+    got = cm.sets[1].coords.cpu().numpy().astype(np.int64)
+
+    def spread(v):
+        v = (v + (1 << 17)).astype(np.uint64) & np.uint64(0x3FFFF)
+        for sh, m in ((32, 0x001F00000000FFFF), (16, 0x001F0000FF0000FF), (8, 0x100F00F00F00F00F), (4, 0x10C30C30C30C30C3), (2, 0x1249249249249249)):
+            v = (v | (v << np.uint64(sh))) & np.uint64(m)
+        return v
+    key = (got[:, 0].astype(np.uint64) << np.uint64(54)) | spread(got[:, 1]) | (spread(got[:, 2]) << np.uint64(1)) | (spread(got[:, 3]) << np.uint64(2))
+    assert (np.diff(key.astype(np.float64)) >= 0).all() and len(np.unique(key)) == len(key)
+    assert np.array_equal(got, c[cm.perm.cpu().numpy()].astype(np.int64))
+    # coarser sets: unique parents, counts equal numpy's
+    for l, ts in ((1, 2), (2, 4)):
+        exp = np.unique(np.concatenate([c[:, :1], (c[:, 1:] // ts) * ts], 1), axis=0)
+        assert cm.sets[ts].n == len(exp)
