@@ -50,15 +50,22 @@ def peaks():
 
 
 class ClockSampler:
-    """SM clock / throttle-reason samples taken DURING the timed region (B200_PROFILING.md 'clocks' line) through NVML,
-    from the benchmark thread itself right after a step has been enqueued (the GPU is still executing it) and outside
-    the CUDA-event pair of any step.  A background poller (nvidia-smi -lms, or an NVML thread) contends with kernel
-    submission and inflated ms_per_step by 45-100% when tried."""
+    """Clock evidence for the timed region (B200_PROFILING.md 'clocks' line) without perturbing it.
+
+    * SM clock: measured ON THE DEVICE between timed steps by `osb_measure_sm_mhz` (cycles of clock64 per ns of
+      %globaltimer over 20 us; a single-thread kernel outside every step's CUDA-event pair).
+    * throttle reasons / max clock: NVML, read immediately before and immediately after the timed region.
+    Why not NVML / nvidia-smi during the region: measured here, a query issued while kernels are in flight -- or even right
+    after a drain -- intermittently stalls the GPU for 30-70 ms (per-step max 34-67 ms against a 4.6 ms median), and a
+    background `nvidia-smi -lms` poller inflated ms/step by 45-100%."""
     REASONS = {'hw_slowdown': 0x8, 'sw_thermal_slowdown': 0x20, 'hw_thermal_slowdown': 0x40, 'sw_power_cap': 0x4}
 
-    def __init__(self, index):
-        self.sm, self.mx, self.reasons, self.power = [], None, set(), []
-        self.ok = False
+    def __init__(self, index, dev):
+        from openscene_b200 import _cabi
+        self.cabi = _cabi
+        self.buf = torch.zeros(64, dtype=torch.float32, device=dev)
+        self.n = 0
+        self.mx, self.reasons, self.ok = None, set(), False
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -69,13 +76,16 @@ class ClockSampler:
             self.err = str(e)
 
     def sample(self):
-        """SM clock + clock-event reasons only: the power query stalls the GPU for tens of milliseconds."""
+        """enqueue one on-device clock measurement (asynchronous, ~20 us of GPU time)."""
+        if self.n < 64:
+            self.cabi.call('osb_measure_sm_mhz', self.cabi.c_void_p(self.buf.data_ptr() + 4 * self.n), self.cabi.stream_ptr())
+            self.n += 1
+
+    def nvml_reasons(self):
         if not self.ok:
             return
-        nv = self.nv
         try:
-            self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
-            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
             for name, bit in self.REASONS.items():
                 if r & bit:
                     self.reasons.add(name)
@@ -83,11 +93,13 @@ class ClockSampler:
             pass
 
     def stop(self):
+        vals = sorted(self.buf[:self.n].cpu().tolist())
+        out = {'sm_mhz': vals[len(vals) // 2] if vals else None, 'sm_max_mhz': self.mx, 'reasons': sorted(self.reasons),
+               'samples': len(vals), 'how': 'sm_mhz: on-device clock64/globaltimer between timed steps; reasons: NVML right before '
+                                            'and right after the timed region'}
         if not self.ok:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvml unavailable: ' + getattr(self, 'err', '')]}
-        return {'sm_mhz': float(np.median(self.sm)) if self.sm else None, 'sm_max_mhz': self.mx,
-                'reasons': sorted(self.reasons), 'samples': len(self.sm),
-                'power_w_max': max(self.power) if self.power else None}
+            out['reasons'] = ['nvml unavailable: ' + getattr(self, 'err', '')]
+        return out
 
 
 def algorithmic_bytes(census):
@@ -234,11 +246,7 @@ def main():
             a.record(); fn(); b.record()
             evs.append((a, b))
             if sampler is not None and i in (k // 4, k // 2, (3 * k) // 4):
-                # An NVML query issued while kernels are in flight stalls the GPU for 20-60 ms (measured: per-step max of
-                # 34-67 ms against a 4.6 ms median), and that lands inside the event pair of the step being executed.
-                # So: drain the stream, query right away (the clock / throttle state of a GPU that was busy microseconds
-                # ago), continue.  The drain is outside every event pair.
-                torch.cuda.synchronize()
+                # on-device clock measurement, stream-ordered between two steps (outside their event pairs)
                 sampler.sample()
         torch.cuda.synchronize()
         gc.enable()
@@ -252,15 +260,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local, dev) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
     l0 = _cabi.lib().osb_launch_count()
     if sampler:
-        sampler.sample()                                       # first NVML calls cost milliseconds: pay them before the timed region
-        sampler.sm.clear(); sampler.power.clear(); sampler.reasons.clear()
+        sampler.nvml_reasons()                                 # throttle reasons right before ...
+        torch.cuda.synchronize()
     ms_dev = timed(step_device, args.steps, sampler, tag='device')
+    if sampler:
+        sampler.nvml_reasons()                                 # ... and right after the timed region
     launches = _cabi.lib().osb_launch_count() - l0
     barrier()
     clocks = sampler.stop() if sampler else None

@@ -47,6 +47,8 @@ const char *osb_last_error(void);
 int osb_device_info(int *sm_count, int *cc_major, int *cc_minor);
 /* number of kernels this library has launched in this process (bench.py's `gpu_launches`). */
 int64_t osb_launch_count(void);
+/* SM clock in MHz measured on the device (clock64 against %globaltimer over ~20 us); *mhz_dev is a device float. */
+int osb_measure_sm_mhz(float *mhz_dev, void *stream);
 
 /* --------------------------------------------------------- coordinate sets
  * A coordinate is an int32 row (b, x, y, z).  Valid range: 0 <= b < 1024, |x|,|y|,|z| < 2^17 - 256.

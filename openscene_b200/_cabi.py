@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libosb200.so')
 _lib = None
 
-P = c_void_p
+P = c_void_p     # noqa: E305 (re-exported as _cabi.c_void_p)
 I32, I64, SZ = c_int32, c_int64, c_size_t
 
 # name -> (restype, argtypes); mirrors include/osb200.h one to one
@@ -20,6 +20,7 @@ SIGNATURES = {
     'osb_last_error': (c_char_p, []),
     'osb_device_info': (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     'osb_launch_count': (I64, []),
+    'osb_measure_sm_mhz': (c_int, [P, P]),
     'osb_coordset_workspace_bytes': (SZ, [I64]),
     'osb_coordset_build': (c_int, [P, I64, P, P, P, P, I64, POINTER(I32), P, SZ, P]),
     'osb_coordset_stride': (c_int, [P, I64, I32, P, P, POINTER(I64), P, SZ, P]),

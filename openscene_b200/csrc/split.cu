@@ -66,3 +66,24 @@ int osb_split_to_f32(const void *in_split, int64_t n, int32_t c, float *out, voi
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// SM clock measured on the device: cycles of clock64() per nanosecond of %globaltimer over ~20 us.
+// bench.py calls it between timed steps: an NVML / nvidia-smi query during the timed region stalls the GPU for
+// tens of milliseconds, this costs one 20 us single-thread kernel outside every step's event pair.
+namespace osb {
+__global__ void k_measure_sm_mhz(float *__restrict__ out) {
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  const long long c0 = clock64();
+  do { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); } while (t1 - t0 < 20000ull);
+  const long long c1 = clock64();
+  *out = (float)((double)(c1 - c0) * 1000.0 / (double)(t1 - t0));
+}
+}  // namespace osb
+
+extern "C" int osb_measure_sm_mhz(float *mhz_dev, void *stream_) {
+  osb::k_measure_sm_mhz<<<1, 1, 0, (cudaStream_t)stream_>>>(mhz_dev);
+  OSB_LAUNCH_CHECK();
+  return 0;
+}
