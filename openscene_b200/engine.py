@@ -74,6 +74,7 @@ class FusedMinkUNet:
         self.out_channels = self.final.cout
         self.last_cm = None
         self._ws = None
+        self._arena = None
         import os
         self.use_pdl = os.environ.get('OSB_PDL', '1') != '0'
         self.use_pyramid = os.environ.get('OSB_PYRAMID', '1') != '0'
@@ -149,9 +150,14 @@ class FusedMinkUNet:
             up_nbr = [d.transposed().nbr for d in down]
             nbr3_a = [t.data_ptr() for t in nbr3]
 
-            arena = torch.empty(self._plan_bytes(n) + 256, dtype=torch.uint8, device=self.device)
-            self._arena = arena                                    # keeps the activations alive until the next forward
-            self._cursor = _al(arena.data_ptr())
+            # Grow-only activation arena reused by every forward (activations never outlive one; the result is a separate
+            # tensor).  Allocating ~1 GB per call made the caching allocator fragment against the 600 MB outputs and fall
+            # back to cudaMalloc inside steps (10-120 ms stalls, 78 of them in 200 steps).
+            need = self._plan_bytes(n) + 256
+            if self._arena is None or self._arena.numel() < need:
+                self._arena = None
+                self._arena = torch.empty(int(need * 1.25), dtype=torch.uint8, device=self.device)
+            self._cursor = _al(self._arena.data_ptr())
             if self._ws is None:
                 self._ws = torch.empty(96 << 20, dtype=torch.uint8, device=self.device)
             self._ws_a, self._ws_bytes = self._ws.data_ptr(), self._ws.numel()
