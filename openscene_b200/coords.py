@@ -48,8 +48,9 @@ class KernelMap:
             nbr_t = torch.empty((self.K, self.n_in), dtype=torch.int32, device=self.nbr.device)
             C.call('osb_kernel_map_transpose', C.ptr(self.nbr), self.n_out, self.K, C.ptr(nbr_t), self.n_in,
                    C.stream_ptr())
+            # no back-reference from the transposed map: a reference cycle would keep both device buffers alive until the
+            # cyclic garbage collector runs (never, inside a gc-disabled serving / benchmark loop)
             self._t = KernelMap(nbr_t, self.K, self.n_out, self.n_in)
-            self._t._t = self
         return self._t
 
     def num_pairs(self):
