@@ -59,3 +59,29 @@ def test_folded_head_scores_match_materialised_path():
     assert (s.float() - s_ref.float()).abs().max() < 2e-3          # both are fp16 roundings of the same cosine
     assert (l == l_ref).float().mean() > 0.99
     assert torch.equal(l, s.float().max(1)[1])
+
+
+def test_steady_state_makes_no_device_allocations():
+    """A serving loop (GC disabled, as in bench.py) must not grow device memory: no reference cycles holding kernel maps,
+    one grow-only activation arena.  Regression test for 10-120 ms cudaMalloc stalls inside steps."""
+    import gc
+    from openscene_b200 import engine, matching
+    c = torch.from_numpy(synth.scene('tiny')).to(DEV)
+    f = torch.ones(c.shape[0], 3, device=DEV)
+    text = torch.from_numpy(synth.text_embeddings(20)).to(DEV)
+    eng = engine.FusedMinkUNet(synth.build_model('MinkUNet18A', 768, seed=0).eval().to(DEV))
+    step = lambda: matching._scores(eng(c, f), None, text, normalize=True)
+    for _ in range(5):
+        step()
+    torch.cuda.synchronize()
+    gc.collect(); gc.disable()
+    try:
+        before = torch.cuda.memory_stats()['num_device_alloc']
+        reserved = torch.cuda.memory_reserved()
+        for _ in range(40):
+            step()
+        torch.cuda.synchronize()
+        assert torch.cuda.memory_stats()['num_device_alloc'] == before
+        assert torch.cuda.memory_reserved() == reserved
+    finally:
+        gc.enable()
