@@ -34,7 +34,7 @@ k_rs_hist(const uint64_t *__restrict__ keys, int64_t n, int shift, int32_t *__re
   hist[(int64_t)threadIdx.x * n_tiles + blockIdx.x] = s_cnt[threadIdx.x];     // digit-major
 }
 
-// exclusive scan of `m` int32 values by one block (m = 256 * n_tiles, a few 10^4 .. 10^5)
+// exclusive scan of `m` int32 values by one block (m = 256 * n_tiles, a few 10^4 .. 10^5); 8 values per thread per round
 static __global__ void __launch_bounds__(1024)
 k_scan_single_block(int32_t *__restrict__ data, int64_t m) {
   __shared__ int32_t s_warp[32];
@@ -42,10 +42,13 @@ k_scan_single_block(int32_t *__restrict__ data, int64_t m) {
   if (threadIdx.x == 0) s_carry = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int64_t base = 0; base < m; base += 1024) {
-    const int64_t i = base + threadIdx.x;
-    const int32_t v = i < m ? data[i] : 0;
-    int32_t x = v;
+  for (int64_t base = 0; base < m; base += 8192) {
+    const int64_t i0 = base + (int64_t)threadIdx.x * 8;
+    int32_t v[8];
+    int32_t tot = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { v[j] = (i0 + j < m) ? data[i0 + j] : 0; tot += v[j]; }
+    int32_t x = tot;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int32_t y = __shfl_up_sync(0xffffffffu, x, o);
@@ -64,8 +67,9 @@ k_scan_single_block(int32_t *__restrict__ data, int64_t m) {
     }
     __syncthreads();
     const int32_t carry = s_carry;
-    const int32_t excl = carry + (warp ? s_warp[warp - 1] : 0) + x - v;
-    if (i < m) data[i] = excl;
+    int32_t run = carry + (warp ? s_warp[warp - 1] : 0) + x - tot;     // exclusive prefix of this thread's first value
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { if (i0 + j < m) data[i0 + j] = run; run += v[j]; }
     __syncthreads();
     if (threadIdx.x == 1023) s_carry = carry + s_warp[31];
     __syncthreads();
