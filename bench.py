@@ -161,8 +161,15 @@ def run_reference(args, rank):
     if rank != 0:
         return
     from openscene_b200 import synth
-    coords = crop_sample(synth.scene(args.workload), 25_000)
+    scene = synth.scene(args.workload)
+    coords = crop_sample(scene, 25_000)
     threads = host_threads()
+    # keep the whole run (warm-up + timed steps) near two minutes whatever K and W the caller asks for: probe one pass,
+    # then shrink the per-step sample (an x-slab of the same scene) if needed
+    t_probe = cpu_pass(coords, args.arch, args.k_text, threads)
+    budget_s, total = 120.0, args.steps + args.warmup
+    if t_probe * total > budget_s:
+        coords = crop_sample(scene, max(4000, int(len(coords) * budget_s / (t_probe * total))))
     for _ in range(args.warmup):
         cpu_pass(coords, args.arch, args.k_text, threads)
     ts = [cpu_pass(coords, args.arch, args.k_text, threads) for _ in range(args.steps)]
