@@ -49,6 +49,7 @@ struct ConvTcParams {
   float *partial;        // [nsplit][n_out][cout_pad] raw accumulators (nsplit > 1)
   const uint8_t *src0_ptr, *src1_ptr;   // raw bases (L2 prefetch of a later tile's own rows)
   int pf_dist;           // tiles ahead to prefetch into L2 (0 = off; only when input rows == output rows)
+  int lazy_idx;          // A producers read the kernel map per offset from global memory; no index prologue, all K offsets run
   int pdl;               // launched with programmatic stream serialization (see osb_conv_fwd_tc flags)
   int dbg_skip;          // tuning only: bit0 = no A gathers, bit1 = no B loads, bit2 = no main loop, bit3 = no stores
   long long *dbg_clock;  // tuning only: per-CTA timestamps [gridDim.x][8] (may be NULL)
@@ -63,7 +64,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
   const int stage_bytes = TC_A_BYTES + p.nt * 128;
   uint8_t *aux = smem + p.stages * stage_bytes;
   int32_t *s_nbr = reinterpret_cast<int32_t *>(aux);                        // [K][128]
-  float *s_scale = reinterpret_cast<float *>(aux + p.K * TC_M * 4);         // [nt]
+  float *s_scale = reinterpret_cast<float *>(aux + (p.lazy_idx ? 0 : p.K * TC_M * 4));   // [nt]
   float *s_shift = s_scale + 256;                                           // [nt]
   uint64_t *bars = reinterpret_cast<uint64_t *>(s_shift + 256);             // full[8], empty[8], accum
   uint32_t *s_misc = reinterpret_cast<uint32_t *>(bars + 17);               // [0] tmem base, [1] kmask
@@ -96,7 +97,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
 
   // ---- prologue: neighbour rows of this tile -> smem, bit mask of offsets that touch the tile.
   // All loads of a thread are issued before any is consumed (22 = ceil(32*128/192) independent loads).
-  {
+  if (!p.lazy_idx) {
     constexpr int PRO = (TC_MAXK * TC_M + TC_THREADS - 1) / TC_THREADS;
     int32_t idx[PRO];
     const int total = p.K * TC_M;
@@ -133,7 +134,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
   // and the shared split workspace belong to the previous kernel in the stream: wait for it to finish and flush.
   if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t tmem_base = s_misc[0];
-  const uint32_t kmask = (p.dbg_skip & 4) ? 0u : s_misc[1];
+  const uint32_t kmask = (p.dbg_skip & 4) ? 0u : (p.lazy_idx ? (p.K >= 32 ? 0xffffffffu : ((1u << p.K) - 1u)) : s_misc[1]);
   if (p.dbg_clock && tid == 64) p.dbg_clock[blockIdx.x * 8 + 1] = clock64();
   const int nb = p.nb0 + p.nb1;
   // stage sequence of this tile = (valid offsets in ascending k) x (channel blocks); split mode takes a chunk
@@ -222,11 +223,29 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
       int s = 0;
       uint32_t phase = 0;
       int t = 0;
+      // lazy mode: this thread's 8 row indices of offset k come straight from the kernel map (L2), prefetched one
+      // offset ahead so that the load latency hides behind the copies of the current offset
+      auto fetch = [&](int k, int32_t (&r)[8]) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int64_t o = row0 + w * 32 + 4 * i + q;
+          r[i] = (o < p.n_out) ? (p.nbr ? __ldg(p.nbr + (int64_t)k * p.n_out + o) : (int32_t)o) : -1;
+        }
+      };
+      int32_t rnext[8];
+      if (p.lazy_idx && kmask) fetch(__ffs(kmask) - 1, rnext);
       for (uint32_t km = kmask; km; km &= km - 1) {
         const int k = __ffs(km) - 1;
         int32_t ridx[8];
+        if (p.lazy_idx) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) ridx[i] = s_nbr[k * TC_M + w * 32 + 4 * i + q];
+          for (int i = 0; i < 8; ++i) ridx[i] = rnext[i];
+          const uint32_t rest = km & (km - 1);
+          if (rest) fetch(__ffs(rest) - 1, rnext);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ridx[i] = s_nbr[k * TC_M + w * 32 + 4 * i + q];
+        }
         for (int cb = 0; cb < nb; ++cb, ++t) {
           if (t < t_begin || t >= t_end) continue;
           mbar_wait(empty0 + 8 * s, phase ^ 1);
@@ -526,7 +545,8 @@ static int g_tc_target_ctas = 148;          // split small launches until ~one C
 static int g_tc_pf_dist = 0;
 static int g_tc_small_nt = 0;              // > 0: N tile used when the launch has few row tiles (tuning)
 static int g_tc_small_rows = 5120;
-static int g_tc_min_stages = 3;            // fewest stages accepted for the multi-CTA-per-SM configuration
+static int g_tc_min_stages = 3;
+static int g_tc_lazy = 1;                  // cp.async path: per-offset index fetch instead of the smem index prologue            // fewest stages accepted for the multi-CTA-per-SM configuration
 static long long *g_tc_dbg_clock = nullptr;
 
 }  // namespace osb
@@ -552,6 +572,7 @@ void osb_debug_set_tc(int use_gather4, int smem_budget) {
 void osb_debug_set_tc3(int pf_dist) { g_tc_pf_dist = pf_dist; }
 void osb_debug_set_tc4(int small_nt, int small_rows) { g_tc_small_nt = small_nt; if (small_rows > 0) g_tc_small_rows = small_rows; }
 void osb_debug_set_tc5(int min_stages) { g_tc_min_stages = min_stages; }
+void osb_debug_set_tc6(int lazy) { g_tc_lazy = lazy; }
 void osb_debug_set_clock(void *buf) { g_tc_dbg_clock = (long long *)buf; }
 void osb_debug_set_tc2(int dbg_skip, int force_split, int target_ctas) {
   if (dbg_skip >= 0) g_tc_dbg_skip = dbg_skip;
@@ -603,7 +624,8 @@ int osb_conv_fwd_tc(const void *src0, int32_t c0, int64_t n_src0, const void *sr
   ConvTcParams p{};
   p.nt = choose_nt(n_out, cp);
   const int stage_bytes = TC_A_BYTES + p.nt * 128;
-  const int aux_bytes = K * TC_M * 4 + 2 * 256 * 4 + 17 * 8 + 64;
+  const int lazy = (g_tc_use_gather4 == 2 && g_tc_lazy) ? 1 : 0;
+  const int aux_bytes = (lazy ? 0 : K * TC_M * 4) + 2 * 256 * 4 + 17 * 8 + 64;
   const int seq = K * (cin / 32);                                         // stages one tile runs through (upper bound)
   int stages = (g_tc_smem_budget - 1024 - aux_bytes) / stage_bytes;      // two CTAs per SM if that leaves >= 3 stages ...
   if (stages < g_tc_min_stages && !(stages == 2 && seq <= 4))            // ... or the whole sequence is that short anyway
@@ -628,6 +650,7 @@ int osb_conv_fwd_tc(const void *src0, int32_t c0, int64_t n_src0, const void *sr
   p.use_gather4 = g_tc_use_gather4;
   p.dbg_skip = g_tc_dbg_skip;
   p.pdl = (flags & 1) ? 1 : 0;
+  p.lazy_idx = lazy;
   p.dbg_clock = g_tc_dbg_clock;
   p.src0_ptr = (const uint8_t *)src0; p.src1_ptr = (const uint8_t *)src1;
   p.pf_dist = (n_src0 == n_out && (c1 == 0 || n_src1 == n_out) && (K & 1)) ? g_tc_pf_dist : 0;

@@ -70,7 +70,7 @@ def conv_stem(x, coords, slots, cap, ks, step, w3, scale=None, shift=None, relu=
     return os_, of_
 
 
-def debug_set_tc(use_gather4=-1, smem_budget=0, dbg_skip=-1, force_split=-1, target_ctas=0, pf_dist=None, small_nt=None, min_stages=None):
+def debug_set_tc(use_gather4=-1, smem_budget=0, dbg_skip=-1, force_split=-1, target_ctas=0, pf_dist=None, small_nt=None, min_stages=None, lazy=None):
     fn = C.lib().osb_debug_set_tc
     fn.restype, fn.argtypes = None, [ctypes.c_int, ctypes.c_int]
     fn(use_gather4, smem_budget)
@@ -89,6 +89,10 @@ def debug_set_tc(use_gather4=-1, smem_budget=0, dbg_skip=-1, force_split=-1, tar
         fn5 = C.lib().osb_debug_set_tc5
         fn5.restype, fn5.argtypes = None, [ctypes.c_int]
         fn5(min_stages)
+    if lazy is not None:
+        fn6 = C.lib().osb_debug_set_tc6
+        fn6.restype, fn6.argtypes = None, [ctypes.c_int]
+        fn6(lazy)
 
 
 def debug_set_clock(buf):

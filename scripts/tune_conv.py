@@ -46,11 +46,16 @@ def case(level, cin, cout, ks, label, **dbg):
     tc.debug_set_tc(**dbg)
     f32 = cout > 256
     us = timeit(lambda: tc.conv_tc(x, cin, None, 0, nbr, n, K, w, cout, None, None, None, True, not f32, f32, None))
-    tc.debug_set_tc(use_gather4=2, smem_budget=112 * 1024, dbg_skip=0, force_split=0, target_ctas=148, pf_dist=0, small_nt=0, min_stages=3)
+    tc.debug_set_tc(use_gather4=2, smem_budget=112 * 1024, dbg_skip=0, force_split=0, target_ctas=148, pf_dist=0, small_nt=0, min_stages=3, lazy=1)
     print(f'{label:46s} L{level} n={n:7d} {cin:3d}->{cout:3d} k{ks}  {us:9.1f} us', flush=True)
 
 
 B2, B1 = 112 * 1024, 226 * 1024
+if len(sys.argv) > 2 and sys.argv[2] == 'lazy':
+    for (lvl, cin, cout, ks) in ((0, 96, 96, 3), (0, 128, 96, 3), (0, 96, 96, 1), (0, 96, 768, 1), (1, 64, 64, 3), (1, 192, 96, 3), (2, 128, 128, 3), (3, 256, 256, 3), (4, 256, 256, 3)):
+        case(lvl, cin, cout, ks, 'smem index prologue', lazy=0)
+        case(lvl, cin, cout, ks, 'lazy per-offset index fetch', lazy=1)
+    sys.exit(0)
 if len(sys.argv) > 2 and sys.argv[2] == 'occ':
     B3, B4 = 75 * 1024, 56 * 1024
     for (lvl, cin, cout, ks) in ((1, 64, 64, 3), (1, 192, 96, 3), (1, 96, 96, 3), (0, 96, 96, 3), (0, 128, 96, 3), (0, 96, 96, 1), (2, 128, 128, 3), (0, 32, 32, 2)):
