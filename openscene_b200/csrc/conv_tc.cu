@@ -624,7 +624,9 @@ int osb_conv_fwd_tc(const void *src0, int32_t c0, int64_t n_src0, const void *sr
   ConvTcParams p{};
   p.nt = choose_nt(n_out, cp);
   const int stage_bytes = TC_A_BYTES + p.nt * 128;
-  const int lazy = (g_tc_use_gather4 == 2 && g_tc_lazy) ? 1 : 0;
+  // lazy index fetch pays off on multi-wave launches (level 0: every tile touches all K offsets, the smem prologue is pure
+  // set-up cost: 325 -> 298 us); on single-wave levels skipping empty (tile, offset) stages wins (59 vs 68 us at level 1)
+  const int lazy = (g_tc_use_gather4 == 2 && g_tc_lazy == 1 && ceil_div(n_out, TC_M) >= 592) || g_tc_lazy == 2 ? 1 : 0;
   const int aux_bytes = (lazy ? 0 : K * TC_M * 4) + 2 * 256 * 4 + 17 * 8 + 64;
   const int seq = K * (cin / 32);                                         // stages one tile runs through (upper bound)
   int stages = (g_tc_smem_budget - 1024 - aux_bytes) / stage_bytes;      // two CTAs per SM if that leaves >= 3 stages ...

@@ -54,7 +54,7 @@ B2, B1 = 112 * 1024, 226 * 1024
 if len(sys.argv) > 2 and sys.argv[2] == 'lazy':
     for (lvl, cin, cout, ks) in ((0, 96, 96, 3), (0, 128, 96, 3), (0, 96, 96, 1), (0, 96, 768, 1), (1, 64, 64, 3), (1, 192, 96, 3), (2, 128, 128, 3), (3, 256, 256, 3), (4, 256, 256, 3)):
         case(lvl, cin, cout, ks, 'smem index prologue', lazy=0)
-        case(lvl, cin, cout, ks, 'lazy per-offset index fetch', lazy=1)
+        case(lvl, cin, cout, ks, 'lazy per-offset index fetch', lazy=2)
     sys.exit(0)
 if len(sys.argv) > 2 and sys.argv[2] == 'occ':
     B3, B4 = 75 * 1024, 56 * 1024
