@@ -78,6 +78,8 @@ class FusedMinkUNet:
         import os
         self.use_pdl = os.environ.get('OSB_PDL', '1') != '0'
         self.use_pyramid = os.environ.get('OSB_PYRAMID', '1') != '0'
+        if 'OSB_TC_LAZY' in os.environ:                      # tuning: 0 = smem index prologue, 1 = lazy on >= 2-wave launches, 2 = always
+            tc.debug_set_tc(lazy=int(os.environ['OSB_TC_LAZY']))
 
     @staticmethod
     def _blocks(seq):
