@@ -151,6 +151,15 @@ int osb_conv_fwd_tc(const void *src0, int32_t c0, int64_t n_src0, const void *sr
                     const float *scale, const float *shift, const void *res, int32_t relu, void *out_split,
                     float *out_f32, const int32_t *out_row_map, void *ws, size_t ws_bytes, int32_t flags, void *stream);
 
+/* Transposed stride-2 convolution (`MinkowskiConvolutionTranspose(kernel_size=2, stride=2)`, models/mink_unet.py:79-101) as a
+ * dense GEMM over the coarse rows followed by a scatter to the children: wpack = osb_conv_pack_weights of the
+ * [1, cin, kvol*cout] matrix (column block k = W[k]); down_nbr = int32 [kvol, n_coarse], the kernel map of the matching
+ * strided convolution (child row of parent o through offset k, -1 if absent).  out_* have one row per FINE voxel and
+ * `cout` channels; every fine row is written exactly once.  scale/shift/relu/flags as osb_conv_fwd_tc. */
+int osb_convtr_fwd_tc(const void *src, int32_t cin, int64_t n_coarse, const int32_t *down_nbr, int32_t kvol, const void *wpack,
+                      int32_t cout, const float *scale, const float *shift, int32_t relu, void *out_split, float *out_f32,
+                      int32_t flags, void *stream);
+
 /* Stem: fused kernel-map probe + conv for tiny cin (<= 3) and cout <= 32, fp32 FMA.  One launch replaces the
  * 5x5x5 map build (125 probes / voxel) and the 3->32 convolution of `conv0p1s1`.
  *   in  fp32 [n, cin] internal order;  w fp32 [K, cin, cout];  epilogue as osb_conv_fwd_tc. */

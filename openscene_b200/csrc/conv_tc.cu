@@ -49,6 +49,8 @@ struct ConvTcParams {
   float *partial;        // [nsplit][n_out][cout_pad] raw accumulators (nsplit > 1)
   const uint8_t *src0_ptr, *src1_ptr;   // raw bases (L2 prefetch of a later tile's own rows)
   int pf_dist;           // tiles ahead to prefetch into L2 (0 = off; only when input rows == output rows)
+  const int32_t *cmap;   // dense transposed conv: per column block k = col / cmap_cout, tile row o goes to row cmap[k*n_out + o] (-1: drop)
+  int cmap_cout;         //   ... and to column col % cmap_cout; outputs then have cmap_cout channels per row
   int lazy_idx;          // A producers read the kernel map per offset from global memory; no index prologue, all K offsets run
   int pdl;               // launched with programmatic stream serialization (see osb_conv_fwd_tc flags)
   int dbg_skip;          // tuning only: bit0 = no A gathers, bit1 = no B loads, bit2 = no main loop, bit3 = no stores
@@ -124,8 +126,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
   }
   for (int n = tid; n < p.nt; n += TC_THREADS) {
     const int c = n0 + n;
-    s_scale[n] = (p.scale && c < p.cout) ? __ldg(p.scale + c) : 1.f;
-    s_shift[n] = (p.shift && c < p.cout) ? __ldg(p.shift + c) : 0.f;
+    const int cc = p.cmap ? c % p.cmap_cout : c;
+    s_scale[n] = (p.scale && c < p.cout) ? __ldg(p.scale + cc) : 1.f;
+    s_shift[n] = (p.shift && c < p.cout) ? __ldg(p.shift + cc) : 0.f;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -341,7 +344,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
         const int r = 4 * i + rsub;
         const int32_t mo = __shfl_sync(0xffffffffu, my_orow, r);
         const int64_t grow = mapped ? (int64_t)mo : wrow0 + r;
-        if (wrow0 + r < p.n_out && !no_store)
+        if (wrow0 + r < p.n_out && !no_store && grow >= 0)
           *reinterpret_cast<uint4 *>(base + grow * row_bytes + col_byte + chunk * 16) = v[i];
       }
     };
@@ -400,6 +403,14 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
 #pragma unroll
         for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
       }
+      int oc0 = c0;                                  // first output channel of this block in the destination row
+      int out_c = p.cout;                            // channels per destination row
+      if (p.cmap) {                                  // dense transposed conv: this column block belongs to child k
+        const int kch = c0 / p.cmap_cout;
+        oc0 = c0 - kch * p.cmap_cout;
+        out_c = p.cmap_cout;
+        my_orow = (o < p.n_out) ? __ldg(p.cmap + (int64_t)kch * p.n_out + o) : -1;
+      }
       if (p.out_split) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -410,7 +421,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
           sts128(my_line + (((4 + g) ^ sw) << 4), *reinterpret_cast<const uint4 *>(ll));
         }
         __syncwarp();
-        flush_tile(p.out_split, (int64_t)p.cout * 4, (int64_t)(c0 >> 5) * 128, false);
+        flush_tile(p.out_split, (int64_t)out_c * 4, (int64_t)(oc0 >> 5) * 128, p.cmap != nullptr);
         __syncwarp();
       }
       if (p.out_f32) {
@@ -419,7 +430,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUte
           sts128(my_line + ((g ^ sw) << 4), make_uint4(__float_as_uint(y[4 * g]), __float_as_uint(y[4 * g + 1]),
                                                        __float_as_uint(y[4 * g + 2]), __float_as_uint(y[4 * g + 3])));
         __syncwarp();
-        flush_tile(reinterpret_cast<uint8_t *>(p.out_f32), (int64_t)p.cout * 4, (int64_t)c0 * 4, p.out_row_map != nullptr);
+        flush_tile(reinterpret_cast<uint8_t *>(p.out_f32), (int64_t)out_c * 4, (int64_t)oc0 * 4, p.out_row_map != nullptr || p.cmap != nullptr);
         __syncwarp();
       }
     }
@@ -606,10 +617,37 @@ int osb_conv_pack_weights(const float *w, int32_t K, int32_t cin, int32_t cout, 
   return 0;
 }
 
+static int conv_fwd_tc_impl(const void *src0, int32_t c0, int64_t n_src0, const void *src1, int32_t c1, int64_t n_src1,
+                            const int32_t *nbr, int64_t n_out, int32_t K, const void *wpack, int32_t cout, const float *scale,
+                            const float *shift, const void *res, int32_t relu, void *out_split, float *out_f32,
+                            const int32_t *out_row_map, void *ws, size_t ws_bytes, int32_t flags, void *stream_,
+                            const int32_t *cmap, int32_t cmap_cout);
+
 int osb_conv_fwd_tc(const void *src0, int32_t c0, int64_t n_src0, const void *src1, int32_t c1, int64_t n_src1,
                     const int32_t *nbr, int64_t n_out, int32_t K, const void *wpack, int32_t cout, const float *scale,
                     const float *shift, const void *res, int32_t relu, void *out_split, float *out_f32,
                     const int32_t *out_row_map, void *ws, size_t ws_bytes, int32_t flags, void *stream_) {
+  return conv_fwd_tc_impl(src0, c0, n_src0, src1, c1, n_src1, nbr, n_out, K, wpack, cout, scale, shift, res, relu, out_split,
+                          out_f32, out_row_map, ws, ws_bytes, flags, stream_, nullptr, 0);
+}
+
+// Transposed stride-2 convolution as a dense GEMM over the COARSE rows: z[o, k*cout + c] = sum_ci x[o, ci] W[k][ci][c]
+// (wpack = osb_conv_pack_weights of the [1, cin, kvol*cout] matrix), whose epilogue sends column block k of coarse row o
+// to the fine row down_nbr[k*n_coarse + o] (the stride-2 kernel map of the matching strided conv; -1 = that child does
+// not exist).  Every fine row has exactly one (parent, k), so each output row is written exactly once.
+int osb_convtr_fwd_tc(const void *src, int32_t cin, int64_t n_coarse, const int32_t *down_nbr, int32_t kvol, const void *wpack,
+                      int32_t cout, const float *scale, const float *shift, int32_t relu, void *out_split, float *out_f32,
+                      int32_t flags, void *stream_) {
+  OSB_CHECK(down_nbr != nullptr && kvol >= 1 && cout % 32 == 0, "osb_convtr_fwd_tc: bad arguments");
+  return conv_fwd_tc_impl(src, cin, n_coarse, nullptr, 0, 0, nullptr, n_coarse, 1, wpack, kvol * cout, scale, shift, nullptr, relu,
+                          out_split, out_f32, nullptr, nullptr, 0, flags, stream_, down_nbr, cout);
+}
+
+static int conv_fwd_tc_impl(const void *src0, int32_t c0, int64_t n_src0, const void *src1, int32_t c1, int64_t n_src1,
+                            const int32_t *nbr, int64_t n_out, int32_t K, const void *wpack, int32_t cout, const float *scale,
+                            const float *shift, const void *res, int32_t relu, void *out_split, float *out_f32,
+                            const int32_t *out_row_map, void *ws, size_t ws_bytes, int32_t flags, void *stream_,
+                            const int32_t *cmap, int32_t cmap_cout) {
   cudaStream_t stream = (cudaStream_t)stream_;
   OSB_CHECK(src0 && c0 > 0 && c0 % 32 == 0 && c1 >= 0 && c1 % 32 == 0, "osb_conv_fwd_tc: channel counts must be multiples of 32 (c0=%d c1=%d)", c0, c1);
   OSB_CHECK((c1 == 0) == (src1 == nullptr), "osb_conv_fwd_tc: src1 / c1 mismatch");
@@ -653,10 +691,11 @@ int osb_conv_fwd_tc(const void *src0, int32_t c0, int64_t n_src0, const void *sr
   p.dbg_skip = g_tc_dbg_skip;
   p.pdl = (flags & 1) ? 1 : 0;
   p.lazy_idx = lazy;
+  p.cmap = cmap; p.cmap_cout = cmap_cout;
   p.dbg_clock = g_tc_dbg_clock;
   p.src0_ptr = (const uint8_t *)src0; p.src1_ptr = (const uint8_t *)src1;
   p.pf_dist = (n_src0 == n_out && (c1 == 0 || n_src1 == n_out) && (K & 1)) ? g_tc_pf_dist : 0;
-  const size_t need = osb_conv_tc_workspace_bytes(n_out, K, cin, cout);
+  const size_t need = cmap ? 0 : osb_conv_tc_workspace_bytes(n_out, K, cin, cout);
   p.nsplit = 1;
   p.partial = nullptr;
   if (need > 0) {

@@ -59,6 +59,8 @@ class FusedMinkUNet:
         if net.training:
             raise RuntimeError("FusedMinkUNet folds BatchNorm running statistics: call model.eval() first")
         self.device = p.device
+        import os
+        self.dense_up = os.environ.get('OSB_DENSE_UP', '1') != '0'
         with torch.cuda.device(self.device), torch.no_grad():
             self.stem = _Conv(net.conv0p1s1, net.bn0, keep_f32=True)
             if self.stem.cin > 3 or self.stem.cout != 32:
@@ -68,7 +70,13 @@ class FusedMinkUNet:
                 down = _Conv(getattr(net, f'conv{i}p{2 ** (i - 1)}s2'), getattr(net, f'bn{i}'))
                 self.enc.append((down, self._blocks(getattr(net, f'block{i}'))))
             for j in range(4, 8):
-                up = _Conv(getattr(net, f'convtr{j}p{2 ** (8 - j)}s2'), getattr(net, f'bntr{j}'))
+                m = getattr(net, f'convtr{j}p{2 ** (8 - j)}s2')
+                up = _Conv(m, getattr(net, f'bntr{j}'))
+                if self.dense_up and up.wpack is not None:
+                    # dense transposed conv: one [cin, 8*cout] matrix, column block k = W[k]
+                    wide = m.kernel.detach().permute(1, 0, 2).reshape(1, up.cin, up.K * up.cout).contiguous()
+                    up.wpack = tc.pack_weights(wide)
+                    up.wpack_a = up.wpack.data_ptr()
                 self.dec.append((up, self._blocks(getattr(net, f'block{j + 1}'))))
             self.final = _Conv(net.final, None, keep_f32=True)
         self.out_channels = self.final.cout
@@ -149,7 +157,7 @@ class FusedMinkUNet:
             n = [cm.sets[t].n for t in ts_list]
             nbr3 = [cm.kernel_map(t, t, 3).nbr for t in ts_list]
             down = [cm.kernel_map(ts_list[l], ts_list[l + 1], 2) for l in range(4)]
-            up_nbr = [d.transposed().nbr for d in down]
+            up_nbr = [d.transposed().nbr for d in down] if not self.dense_up else None
             nbr3_a = [t.data_ptr() for t in nbr3]
 
             # Grow-only activation arena reused by every forward (activations never outlive one; the result is a separate
@@ -186,7 +194,15 @@ class FusedMinkUNet:
                 skips.append(cur)
             for j, (uconv, blocks) in enumerate(self.dec):
                 l = 3 - j                                   # output level of this transposed conv
-                y = self._conv(uconv, [cur], up_nbr[l].data_ptr(), n[l])
+                if self.dense_up:
+                    y = self._cursor
+                    self._cursor += _al(n[l] * 4 * uconv.cout)
+                    rc = C.lib().osb_convtr_fwd_tc(cur[0], cur[1], n[l + 1], down[l].nbr.data_ptr(), uconv.K, uconv.wpack_a,
+                                                   uconv.cout, uconv.scale_a, uconv.shift_a, 1, y, 0, self._flags, self._stream)
+                    if rc:
+                        C.check(rc, 'osb_convtr_fwd_tc')
+                else:
+                    y = self._conv(uconv, [cur], up_nbr[l].data_ptr(), n[l])
                 cur = self._stage(blocks, [(y, uconv.cout, n[l]), skips[l]], nbr3_a[l], n[l])
             if head is not None:                           # folded head: 96 -> (96 + K) conv, rows straight in caller order
                 z = torch.empty((n[0], head.cout), dtype=torch.float32, device=self.device)
