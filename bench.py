@@ -302,22 +302,23 @@ def main():
     # ---- dominant kernel (k_conv_tc) timed live with CUDA events on the launching stream -------------
     conv_ms, conv_calls = 0.0, 0
     if not args.modules:
-        real_fn = _cabi.lib().osb_conv_fwd_tc
         pend = []
+        hooked_names = ('osb_conv_fwd_tc', 'osb_convtr_fwd_tc')          # every launch of k_conv_tc goes through these two
 
-        class Hooked:                      # the engine calls lib().osb_conv_fwd_tc(...) directly with raw addresses
-            def __call__(self, *a):
+        def make_hook(real_fn):
+            def hooked(*a):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(); r = real_fn(*a); e1.record()
                 pend.append((e0, e1))
                 return r
+            return hooked
         reps = 3
-        hooked = Hooked()
         orig_lib = _cabi.lib
+        hooks = {nm: make_hook(getattr(orig_lib(), nm)) for nm in hooked_names}
 
-        class LibProxy:
+        class LibProxy:                    # the engine calls lib().<fn>(...) directly with raw addresses
             def __getattr__(self, name):
-                return hooked if name == 'osb_conv_fwd_tc' else getattr(orig_lib(), name)
+                return hooks[name] if name in hooks else getattr(orig_lib(), name)
         engine.C.lib = lambda: LibProxy()
         for _ in range(reps):
             flush.zero_()
