@@ -17,6 +17,11 @@
  *        `torch.max(pred,1)` (run/evaluate.py:288-323).
  *   osb_voxelize_*                      `Voxelizer.voxelize` + `sparse_quantize`/`fnv_hash_vec`
  *        (dataset/voxelizer.py:97-140, dataset/voxelization_utils.py:9-22,44-137).
+ *   osb_fusion_*                        the multi-view fusion loop: `PointCloudToImageMapper.compute_mapping`
+ *        (scripts/feature_fusion/fusion_util.py:102-139) + the running mean of
+ *        scripts/feature_fusion/scannet_openseg.py:74-108.
+ *   osb_confusion_* / osb_intersection_union   `confusion_matrix` (util/metric.py:9-25) and
+ *        `intersectionAndUnionGPU` (util/util.py:132-145).
  *
  * Conventions
  *   - every pointer is a raw DEVICE pointer unless the name ends in `_host`;
@@ -211,6 +216,40 @@ size_t osb_voxelize_workspace_bytes(int64_t n);
 int osb_voxelize(const void *coords, int32_t coords_is_f64, int64_t n, const double *matrix_host,
                  int32_t *coords_vox, int64_t *inds, int64_t *inds_reverse, int64_t *n_vox_host,
                  double *min_host, void *ws, size_t ws_bytes, void *stream);
+
+/* ------------------------------------------------------------- multi-view feature fusion (8f rank 2)
+ * One call handles a batch of 1..32 frames, in frame order.
+ *   points   fp32 or fp64 [n,3] world coordinates
+ *   w2c      fp64 [F,16]  row-major world-to-camera matrices (= inv(pose), fusion_util.py:120)
+ *   intr     fp64 [F,4]   (fx, fy, cx, cy) per frame (intrinsic[0][0], [1][1], [0][2], [1][2])
+ *   depth    fp64 [F,H,W] metres, or NULL (then the test is p_z > 0, fusion_util.py:134)
+ *   feat     fp16 [F,H,W,C] per-pixel features (the memory the reference holds as a permuted [C,H,W] view),
+ *            C % 8 == 0, C <= 1024
+ *   sum      in/out fp32 [n,C]; counter in/out fp32 [n]: sum += feature, counter += 1 for every frame that sees the
+ *            point, applied in frame order (bit-identical to the reference's per-frame fp32 adds).
+ *            sum == NULL computes the mapping only.
+ *   mapping  out int32 [F,n,3] = (row v, col u, visible) as compute_mapping returns it, or NULL
+ *   ws       osb_fusion_workspace_bytes(n, F) bytes */
+size_t osb_fusion_workspace_bytes(int64_t n, int32_t n_frames);
+int osb_fusion_accumulate(const void *points, int32_t points_is_f64, int64_t n, const double *w2c, const double *intr,
+                          const double *depth, const void *feat, int32_t n_frames, int32_t H, int32_t W, int32_t C,
+                          int32_t cut_bound, double vis_thres, float *sum, float *counter, int32_t *mapping, void *ws,
+                          size_t ws_bytes, void *stream);
+/* feat_bank = sum / (counter == 0 ? 1e-5 : counter)   (scannet_openseg.py:104-105); feat_bank may alias sum */
+int osb_fusion_finalize(const float *sum, const float *counter, int64_t n, int32_t C, float *feat_bank, void *stream);
+
+/* ------------------------------------------------------------- segmentation metrics (8f rank 4)
+ * confusion  in/out uint64 [(C+1),(C+1)], rows = prediction, columns = ground truth; points with gt == ignore_id are
+ *            skipped, predictions equal to nofeat_id land in row C (util/metric.py:13-20; the caller slices [:C,:C]).
+ * bad_labels in/out int32 [1]: number of labels outside the valid range (the reference would raise in reshape).
+ * Labels are int32 or int64 device arrays. */
+int osb_confusion_accumulate(const void *pred, const void *gt, int32_t labels_are_i64, int64_t n, int32_t num_classes,
+                             int32_t ignore_id, int32_t nofeat_id, uint64_t *confusion, int32_t *bad_labels, void *stream);
+/* areas in/out uint64 [3,K] = (intersection, output area, target area) with the reference's histc semantics
+ * (util/util.py:132-145): where target == ignore_id the prediction is ignored too; labels outside 0..K-1 are dropped.
+ * union = output + target - intersection. */
+int osb_intersection_union(const void *output, const void *target, int32_t labels_are_i64, int64_t n, int32_t K,
+                           int32_t ignore_id, uint64_t *areas, void *stream);
 
 #ifdef __cplusplus
 }

@@ -124,3 +124,48 @@ def build_model(arch='MinkUNet18A', out_channels=768, seed=0, ME=None, in_channe
     model = mink_unet(in_channels=in_channels, out_channels=out_channels, D=3, arch=arch, ME=ME)
     randomize_bn_stats(model, seed + 1)
     return model
+
+
+def fusion_case(seed, n, with_depth, image_dim=(320, 240), n_frames=3):
+    """Seeded points on the faces of a room, cameras inside it, depth = z-buffer of the points (mm, uint16) / 1000.
+    Used by scripts/make_golden.py and the tests (which regenerate the inputs and compare with the stored reference outputs)."""
+    rng = np.random.RandomState(seed)
+    ext = np.array([4.0, 3.0, 2.5])
+    pts = rng.rand(n, 3) * ext
+    face = rng.randint(0, 5, n)                           # floor + 4 walls
+    pts[face == 0, 2] = 0.0
+    pts[face == 1, 0] = 0.0
+    pts[face == 2, 0] = ext[0]
+    pts[face == 3, 1] = 0.0
+    pts[face == 4, 1] = ext[1]
+    box = rng.rand(n) < 0.25                              # a box in the middle that occludes the walls behind it
+    pts[box] = np.array([1.5, 1.0, 0.0]) + rng.rand(int(box.sum()), 3) * np.array([1.0, 0.8, 1.2])
+    pts += rng.randn(n, 3) * 0.004
+    W, H = image_dim
+    intr = np.eye(4)
+    intr[0, 0], intr[1, 1], intr[0, 2], intr[1, 2] = 577.870605 * 0.5, 577.870605 * 0.5, (W - 1) * 0.5, (H - 1) * 0.5
+    poses, depths = [], []
+    for f in range(n_frames):
+        eye = np.array([0.4, 0.4, 1.2]) + rng.rand(3) * np.array([3.2, 2.2, 0.6])
+        tgt = rng.rand(3) * ext * np.array([1, 1, 0.6])
+        fwd = (tgt - eye) / np.linalg.norm(tgt - eye)
+        right = np.cross(fwd, np.array([0, 0, 1.0]))
+        right /= np.linalg.norm(right)
+        down = np.cross(fwd, right)
+        c2w = np.eye(4)
+        c2w[:3, 0], c2w[:3, 1], c2w[:3, 2], c2w[:3, 3] = right, down, fwd, eye
+        poses.append(c2w)
+        if with_depth:
+            pc = (np.linalg.inv(c2w) @ np.concatenate([pts, np.ones((n, 1))], 1).T)
+            z = pc[2]
+            ok = z > 0.05
+            u = np.round(pc[0, ok] * intr[0, 0] / z[ok] + intr[0, 2]).astype(int)
+            v = np.round(pc[1, ok] * intr[1, 1] / z[ok] + intr[1, 2]).astype(int)
+            inb = (u >= 0) & (u < W) & (v >= 0) & (v < H)
+            zb = np.full((H, W), np.inf)
+            np.minimum.at(zb, (v[inb], u[inb]), z[ok][inb])
+            zb[~np.isfinite(zb)] = 0.0                    # holes: invalid depth, as in a real sensor image
+            depths.append(np.round(zb * 1000.0).astype(np.uint16) / 1000.0)      # imread(uint16 png) / depth_scale
+        else:
+            depths.append(None)
+    return pts, poses, depths, intr

@@ -7,7 +7,13 @@
    statistics, on a small synthetic room.  These pin the *topology*; the ME arithmetic itself is the oracle's
    (parity unpinned against real MinkowskiEngine -- see oracle/__init__.py).
 
-Usage: python scripts/make_golden.py
+3. fusion_mapping_*.npz : outputs of the reference's own ``PointCloudToImageMapper.compute_mapping``
+   (scripts/feature_fusion/fusion_util.py, imported with a stub ``tensorflow`` the method never touches) for seeded
+   points, camera poses and z-buffer depth images.
+4. metric_*.npz    : outputs of the reference's ``util/metric.py`` and ``util/util.py`` intersection/union helpers
+   (stub ``open3d`` / ``clip`` / ``matplotlib``; ``Tensor.cuda`` patched to the identity -- no GPU here).
+
+Usage: python scripts/make_golden.py [voxelizer] [unet] [fusion] [metric]
 """
 import collections
 import collections.abc
@@ -84,7 +90,69 @@ def golden_unet():
         print(arch, 'params', sum(p.numel() for p in model.parameters()), 'out', out.shape, 'abs mean', np.abs(out).mean())
 
 
+def _stub_modules(*names):
+    import types
+    for nm in names:
+        parts = nm.split('.')
+        for i in range(1, len(parts) + 1):
+            sub = '.'.join(parts[:i])
+            if sub not in sys.modules:
+                sys.modules[sub] = types.ModuleType(sub)
+            if i > 1:
+                setattr(sys.modules['.'.join(parts[:i - 1])], parts[i - 1], sys.modules[sub])
+
+
+def golden_fusion():
+    _stub_modules('tensorflow', 'tensorflow.io', 'tensorflow.compat', 'tensorflow.compat.v1')
+    sys.path.insert(0, os.path.join(REF, 'scripts', 'feature_fusion'))
+    from fusion_util import PointCloudToImageMapper
+    from openscene_b200.synth import fusion_case
+    cases = {'depth_cut10': dict(seed=21, n=6000, with_depth=True, cut=10),
+             'depth_cut0': dict(seed=22, n=5000, with_depth=True, cut=0),
+             'nodepth_cut5': dict(seed=23, n=5000, with_depth=False, cut=5)}
+    for name, c in cases.items():
+        pts, poses, depths, intr = fusion_case(c['seed'], c['n'], c['with_depth'])
+        mapper = PointCloudToImageMapper(image_dim=(320, 240), intrinsics=intr, visibility_threshold=0.25, cut_bound=c['cut'])
+        maps = np.stack([mapper.compute_mapping(p, pts, d) for p, d in zip(poses, depths)])
+        np.savez_compressed(os.path.join(OUT, f'fusion_mapping_{name}.npz'), seed=c['seed'], n=c['n'], with_depth=c['with_depth'],
+                            cut=c['cut'], mapping=maps.astype(np.int32))
+        print('fusion', name, 'visible per frame', maps[:, :, 2].sum(1))
+
+
+def golden_metric():
+    _stub_modules('open3d', 'clip', 'matplotlib', 'matplotlib.patches', 'matplotlib.pyplot')
+    sys.path.insert(0, REF)
+    from util import metric as ref_metric
+    from util import util as ref_util
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        for name, (C, ds, seed, nofeat) in {'scannet20': (20, 'scannet_3d', 31, False), 'mp160_nofeat': (160, 'matterport_3d_160', 32, True),
+                                            'nuscenes16': (16, 'nuscenes_3d', 33, False)}.items():
+            rng = np.random.RandomState(seed)
+            n = 50000
+            gt = rng.randint(0, C, n)
+            gt[rng.rand(n) < 0.1] = 255
+            gt[gt == 3] = 5                                      # a class that never occurs in gt
+            pred = np.where(rng.rand(n) < 0.6, np.minimum(gt, C - 1), rng.randint(0, C, n))
+            if nofeat:
+                pred[rng.rand(n) < 0.05] = 256
+            conf = ref_metric.confusion_matrix(pred.copy(), gt.copy(), C)
+            miou = ref_metric.evaluate(pred.copy(), gt.copy(), stdout=False, dataset=ds)
+            out = dict(pred=pred.astype(np.int32), gt=gt.astype(np.int32), C=C, confusion=conf.astype(np.int64), miou=np.float64(miou))
+            if not nofeat:
+                i_np, u_np, t_np = ref_util.intersectionAndUnion(pred.copy(), gt.copy(), C, 255)
+                i_t, u_t, t_t = ref_util.intersectionAndUnionGPU(torch.from_numpy(pred.copy()), torch.from_numpy(gt.copy()), C, 255)
+                assert np.array_equal(i_np, i_t.numpy()) and np.array_equal(u_np, u_t.numpy()) and np.array_equal(t_np, t_t.numpy())
+                out.update(inter=i_np.astype(np.int64), union=u_np.astype(np.int64), target=t_np.astype(np.int64))
+            np.savez_compressed(os.path.join(OUT, f'metric_{name}.npz'), **out)
+            print('metric', name, 'mIoU', miou)
+    finally:
+        torch.Tensor.cuda = orig_cuda
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
-    golden_voxelizer()
-    golden_unet()
+    todo = sys.argv[1:] or ['voxelizer', 'unet', 'fusion', 'metric']
+    for nm in todo:
+        {'voxelizer': golden_voxelizer, 'unet': golden_unet, 'fusion': golden_fusion, 'metric': golden_metric}[nm]()
