@@ -20,6 +20,8 @@
  *   osb_fusion_*                        the multi-view fusion loop: `PointCloudToImageMapper.compute_mapping`
  *        (scripts/feature_fusion/fusion_util.py:102-139) + the running mean of
  *        scripts/feature_fusion/scannet_openseg.py:74-108.
+ *   osb_feature_remap                   the fused-feature index remap of `FusedFeatureLoader.__getitem__`
+ *        (dataset/feature_loader.py:101-172).
  *   osb_confusion_* / osb_intersection_union   `confusion_matrix` (util/metric.py:9-25) and
  *        `intersectionAndUnionGPU` (util/util.py:132-145).
  *
@@ -250,6 +252,21 @@ int osb_confusion_accumulate(const void *pred, const void *gt, int32_t labels_ar
  * union = output + target - intersection. */
 int osb_intersection_union(const void *output, const void *target, int32_t labels_are_i64, int64_t n, int32_t K,
                            int32_t ignore_id, uint64_t *areas, void *stream);
+
+/* ------------------------------------------------------------- fused-feature remap after voxelisation (8f rank 3)
+ * The fused 2-D features of a scene are stored as {feat [M,C], mask_full bool [n_pts]} with one feat row per True
+ * entry of mask_full, in point order (scripts/feature_fusion/fusion_util.py:87-89).  Given the voxeliser's
+ * representative point per voxel (vox_ind), produce what dataset/feature_loader.py:101-172 hands to the model:
+ *   mask_vox  out uint8 [n_vox]            mask_full[vox_ind]                                  (:127)
+ *   feat_out  out [<= n_vox, row_bytes]    keep_all == 0 (train): rows of the voxels with mask_vox set, in voxel
+ *                                          order (:128-145); keep_all != 0 (val / test): one row per voxel, zeros
+ *                                          where the voxel has no feature (:107-111,167-170)
+ *   n_out_host out int64 [1] HOST          rows written
+ * Rows are opaque: row_bytes = C * element size, a multiple of 16.  m_rows must equal popcount(mask_full).  SYNC. */
+size_t osb_feature_remap_workspace_bytes(int64_t n_pts, int64_t n_vox);
+int osb_feature_remap(const uint8_t *mask_full, int64_t n_pts, const int64_t *vox_ind, int64_t n_vox, const void *feat,
+                      int64_t m_rows, int32_t row_bytes, int32_t keep_all, uint8_t *mask_vox, void *feat_out,
+                      int64_t *n_out_host, void *ws, size_t ws_bytes, void *stream);
 
 #ifdef __cplusplus
 }

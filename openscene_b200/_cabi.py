@@ -47,6 +47,8 @@ SIGNATURES = {
     'osb_fusion_workspace_bytes': (SZ, [I64, I32]),
     'osb_fusion_accumulate': (c_int, [P, I32, I64, P, P, P, P, I32, I32, I32, I32, I32, c_double, P, P, P, P, SZ, P]),
     'osb_fusion_finalize': (c_int, [P, P, I64, I32, P, P]),
+    'osb_feature_remap_workspace_bytes': (SZ, [I64, I64]),
+    'osb_feature_remap': (c_int, [P, I64, P, I64, P, I64, I32, I32, P, P, POINTER(I64), P, SZ, P]),
     'osb_confusion_accumulate': (c_int, [P, P, I32, I64, I32, I32, I32, P, P, P]),
     'osb_intersection_union': (c_int, [P, P, I32, I64, I32, I32, P, P]),
 }

@@ -13,7 +13,11 @@
 4. metric_*.npz    : outputs of the reference's ``util/metric.py`` and ``util/util.py`` intersection/union helpers
    (stub ``open3d`` / ``clip`` / ``matplotlib``; ``Tensor.cuda`` patched to the identity -- no GPU here).
 
-Usage: python scripts/make_golden.py [voxelizer] [unet] [fusion] [metric]
+5. loader_*.npz    : what the reference's own ``FusedFeatureLoader.__getitem__`` (dataset/feature_loader.py) returns for
+   synthetic scene / fused-feature files written to a scratch directory (``SharedArray`` stubbed; ``torch.load`` given
+   the ``weights_only=False`` default of the PyTorch the reference targets), plus the 4x4 matrix its voxeliser drew.
+
+Usage: python scripts/make_golden.py [voxelizer] [unet] [fusion] [metric] [loader]
 """
 import collections
 import collections.abc
@@ -151,8 +155,65 @@ def golden_metric():
         torch.Tensor.cuda = orig_cuda
 
 
+def golden_loader():
+    import functools
+    import shutil
+    import tempfile
+    collections.Sequence = collections.abc.Sequence
+    collections.Iterable = collections.abc.Iterable
+    _stub_modules('SharedArray')
+    sys.path.insert(0, REF)
+    from dataset.feature_loader import FusedFeatureLoader
+    orig_load = torch.load
+    torch.load = functools.partial(orig_load, weights_only=False)
+    tmp = tempfile.mkdtemp(prefix='osb_golden_')
+    try:
+        cases = {'train': dict(split='train', seed=51, legacy=False), 'val': dict(split='val', seed=52, legacy=False),
+                 'train_legacy': dict(split='train', seed=53, legacy=True)}
+        for name, c in cases.items():
+            rng = np.random.RandomState(c['seed'])
+            n, C = 3000, 16
+            locs = (rng.rand(n, 3) * np.array([1.2, 1.0, 0.8])).astype(np.float32)
+            colors = (rng.rand(n, 3) * 2 - 1).astype(np.float32)
+            labels = rng.randint(0, 20, n).astype(np.float64)
+            labels[rng.rand(n) < 0.1] = -100
+            root = os.path.join(tmp, name, 'scannet_3d')
+            os.makedirs(os.path.join(root, c['split']))
+            featdir = os.path.join(tmp, name, 'feat')
+            os.makedirs(featdir)
+            torch.save((locs, colors, labels), os.path.join(root, c['split'], 'scene0000_00_vh_clean_2.pth'))
+            mask_full = torch.from_numpy(rng.rand(n) < 0.4)
+            M = int(mask_full.sum())
+            feat = torch.from_numpy(rng.randn(M, C).astype(np.float16))
+            blob = {'feat': feat, 'mask_full': mask_full}
+            legacy_mask = None
+            if c['legacy']:
+                legacy_mask = torch.from_numpy(rng.rand(M) < 0.7)
+                blob = {'feat': feat, 'mask': legacy_mask.nonzero()[:, 0], 'mask_full': mask_full}
+            torch.save(blob, os.path.join(featdir, 'scene0000_00_0.pt'))
+            loader = FusedFeatureLoader(datapath_prefix=root, datapath_prefix_feat=featdir, voxel_size=0.05, split=c['split'],
+                                        aug=False, memcache_init=False, eval_all=(c['split'] != 'train'), input_color=False)
+            np.random.seed(c['seed'] + 100)
+            M_v, M_r = loader.voxelizer.get_transformation_matrix()
+            np.random.seed(c['seed'] + 100)                       # same draws inside __getitem__ -> voxelize()
+            item = loader[0]
+            coords, feats, lab, feat_3d, mask = item[:5]
+            out = dict(locs=locs, labels_in=labels, mask_full=mask_full.numpy(), feat=feat.numpy(), matrix=M_r @ M_v,
+                       coords=coords.numpy(), feats=feats.numpy(), labels=lab.numpy(), feat_3d=feat_3d.numpy(), mask=mask.numpy(),
+                       split=c['split'])
+            if legacy_mask is not None:
+                out['legacy_mask'] = legacy_mask.numpy()
+            if len(item) > 5:
+                out['inds_reverse'] = item[5].numpy()
+            np.savez_compressed(os.path.join(OUT, f'loader_{name}.npz'), **out)
+            print('loader', name, 'voxels', coords.shape[0], 'feat rows', feat_3d.shape[0], 'mask true', int(mask.sum()))
+    finally:
+        torch.load = orig_load
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
-    todo = sys.argv[1:] or ['voxelizer', 'unet', 'fusion', 'metric']
+    todo = sys.argv[1:] or ['voxelizer', 'unet', 'fusion', 'metric', 'loader']
     for nm in todo:
-        {'voxelizer': golden_voxelizer, 'unet': golden_unet, 'fusion': golden_fusion, 'metric': golden_metric}[nm]()
+        {'voxelizer': golden_voxelizer, 'unet': golden_unet, 'fusion': golden_fusion, 'metric': golden_metric, 'loader': golden_loader}[nm]()

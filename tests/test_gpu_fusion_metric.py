@@ -143,3 +143,38 @@ def test_fusion_fullsize_properties():
     fb = (F - 1) - vis[:, twice].flip(0).float().argmax(0)
     want2 = (feats[fa, maps[fa, twice, 0], maps[fa, twice, 1]].float() + feats[fb, maps[fb, twice, 0], maps[fb, twice, 1]].float()) / 2.0
     assert torch.equal(bank[twice], want2)
+
+
+@pytest.mark.parametrize('case', ['train', 'val', 'train_legacy'])
+def test_loader_remap_matches_reference_loader(case):
+    """GPU voxeliser + GPU remap == what the reference's FusedFeatureLoader.__getitem__ returned (tests/golden)."""
+    from openscene_b200.fused_features import remap_fused_features
+    from openscene_b200.voxelize import voxelize_points
+    g = golden(f'loader_{case}.npz')
+    cv, inds, inv, _ = voxelize_points(torch.from_numpy(g['locs']).to(DEV), g['matrix'])
+    assert np.array_equal(cv.cpu().numpy(), g['coords'][:, 1:])
+    legacy = g['legacy_mask'] if 'legacy_mask' in g.files else None
+    feat, mask = remap_fused_features(g['feat'], g['mask_full'], inds, str(g['split']), legacy, device=DEV)
+    assert mask.dtype == torch.bool and np.array_equal(mask.cpu().numpy(), g['mask'])
+    assert feat.dtype == torch.float16 and np.array_equal(feat.cpu().numpy(), g['feat_3d'])
+
+
+def test_loader_remap_fullsize_and_errors():
+    from openscene_b200.fused_features import remap_fused_features
+    from oracle import loader_ref
+    g = torch.Generator().manual_seed(9)
+    n_pts, n_vox, c = 1_000_000, 600_000, 768
+    mask_full = torch.rand(n_pts, generator=g) < 0.02                       # 20k supervised points, as the train chunks
+    m = int(mask_full.sum())
+    feat = torch.randn(m, c, generator=g).half()
+    vox_ind = torch.randperm(n_pts, generator=g)[:n_vox]
+    for split in ('train', 'val'):
+        f, mk = remap_fused_features(feat, mask_full, vox_ind, split, device=DEV)
+        fr, mr = loader_ref.remap_fused_features(feat, mask_full, vox_ind, split)
+        assert torch.equal(mk.cpu(), mr) and torch.equal(f.cpu(), fr)
+    with pytest.raises(RuntimeError, match='True entries'):
+        remap_fused_features(feat[:-1], mask_full, vox_ind, 'train', device=DEV)
+    with pytest.raises(RuntimeError, match='outside'):
+        remap_fused_features(feat, mask_full, torch.tensor([0, n_pts]), 'train', device=DEV)
+    f, mk = remap_fused_features(feat, mask_full, torch.zeros(0, dtype=torch.int64), 'train', device=DEV)
+    assert f.shape == (0, c) and mk.numel() == 0

@@ -50,3 +50,18 @@ def test_metric_restatement_matches_reference(case):
     if 'inter' in g.files:
         i, u, t = metric_ref.intersection_and_union(g['pred'], g['gt'], C)
         assert np.array_equal(i, g['inter']) and np.array_equal(u, g['union']) and np.array_equal(t, g['target'])
+
+
+@pytest.mark.parametrize('case', ['train', 'val', 'train_legacy'])
+def test_loader_remap_restatement_matches_reference(case):
+    """oracle voxeliser + oracle remap == what the reference's FusedFeatureLoader.__getitem__ returned."""
+    from oracle import loader_ref, voxelize_ref
+    g = golden(f'loader_{case}.npz')
+    cv, inds, inv, _ = voxelize_ref.voxelize(g['locs'], g['matrix'])
+    assert np.array_equal(cv.astype(np.int32), g['coords'][:, 1:]) and np.all(g['coords'][:, 0] == 1)
+    legacy = torch.from_numpy(g['legacy_mask']) if 'legacy_mask' in g.files else None
+    feat, mask = loader_ref.remap_fused_features(torch.from_numpy(g['feat']), torch.from_numpy(g['mask_full']), inds, str(g['split']), legacy)
+    assert np.array_equal(mask.numpy(), g['mask'])
+    assert feat.dtype == torch.float16 and np.array_equal(feat.numpy(), g['feat_3d'])
+    if 'inds_reverse' in g.files:
+        assert np.array_equal(inv, g['inds_reverse'])
