@@ -72,7 +72,10 @@ size_t osb_coordset_workspace_bytes(int64_t n);
  *   perm        out int32 [n]     internal row -> caller row
  *   inv_perm    out int32 [n]     caller row  -> internal row
  *   slots       out 16B  [cap]    hash table over coords_int
- *   status_host out int32 [2]     HOST: [0] bit0 = coordinate out of range, bit1 = duplicate coordinate
+ *   status_host out int32 [6]     HOST: [0] bit0 = coordinate out of range, bit1 = duplicate coordinate; [1] reserved;
+ *                                 [2..5] = OR (lo, hi word) and AND (lo, hi word) of the 64-bit Morton keys
+ *                                 b<<54 | interleave(x+2^17, y+2^17, z+2^17) -- sizes the occupancy grid below
+ *   slots may be NULL (no hash table wanted: the caller uses an occupancy grid)
  * SYNC: waits for `stream` to deliver status_host. */
 int osb_coordset_build(const int32_t *coords, int64_t n, int32_t *coords_int, int32_t *perm, int32_t *inv_perm,
                        void *slots, int64_t cap, int32_t *status_host, void *ws, size_t ws_bytes, void *stream);
@@ -218,6 +221,26 @@ size_t osb_voxelize_workspace_bytes(int64_t n);
 int osb_voxelize(const void *coords, int32_t coords_is_f64, int64_t n, const double *matrix_host,
                  int32_t *coords_vox, int64_t *inds, int64_t *inds_reverse, int64_t *n_vox_host,
                  double *min_host, void *ws, size_t ws_bytes, void *stream);
+
+/* ------------------------------------------------------------- occupancy grid (alternative to the hash table)
+ * For a coordinate set whose coordinates are all >= 0 and < (2^nbits << log2_ts): one bit per cell of a 2^nbits cube per
+ * batch index, cells in Morton order, + the first row of every 64-cell word.  Because the rows of a set are Morton
+ * sorted, row(cell) = first_row[word] + popcount(bits below): a neighbour lookup is two loads from a table of a few
+ * MB shared by nearby voxels instead of a probe chain.  Limits: 2 <= nbits <= 9, n_batch << (3 nbits) <= 2^27 cells.
+ *   grid        osb_occgrid_bytes(nbits, n_batch) bytes (0 = not representable: use the hash)
+ *   coords_int  the set in internal (Morton) order, as produced by osb_coordset_build / _pyramid
+ *   status_dev  in/out int32 [1] DEVICE: bit0 set if a coordinate fell outside the grid
+ * osb_kernel_map_build_grid / osb_conv_stem_fused_grid are osb_kernel_map_build / osb_conv_stem_fused with the grid of
+ * the INPUT set in place of its hash table; results are identical. */
+size_t osb_occgrid_bytes(int32_t nbits, int32_t n_batch);
+int osb_occgrid_build(const int32_t *coords_int, int64_t n, int32_t log2_ts, int32_t nbits, int32_t n_batch, void *grid,
+                      int32_t *status_dev, void *stream);
+int osb_kernel_map_build_grid(const int32_t *coords_out, int64_t n_out, const void *grid, int32_t log2_ts, int32_t nbits,
+                              int32_t n_batch, int32_t ks_x, int32_t ks_y, int32_t ks_z, int32_t step, int32_t *nbr,
+                              int32_t *pairs_per_k, void *stream);
+int osb_conv_stem_fused_grid(const float *in, int32_t cin, const int32_t *coords, int64_t n, const void *grid, int32_t log2_ts,
+                             int32_t nbits, int32_t n_batch, int32_t ks, int32_t step, const float *w, int32_t cout,
+                             const float *scale, const float *shift, int32_t relu, void *out_split, float *out_f32, void *stream);
 
 /* ------------------------------------------------------------- multi-view feature fusion (8f rank 2)
  * One call handles a batch of 1..32 frames, in frame order.

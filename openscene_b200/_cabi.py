@@ -44,6 +44,10 @@ SIGNATURES = {
     'osb_folded_head_finish': (c_int, [P, I64, I32, I32, I32, P, P, P, P]),
     'osb_voxelize_workspace_bytes': (SZ, [I64]),
     'osb_voxelize': (c_int, [P, I32, I64, POINTER(c_double), P, P, P, POINTER(I64), POINTER(c_double), P, SZ, P]),
+    'osb_occgrid_bytes': (SZ, [I32, I32]),
+    'osb_occgrid_build': (c_int, [P, I64, I32, I32, I32, P, P, P]),
+    'osb_kernel_map_build_grid': (c_int, [P, I64, P, I32, I32, I32, I32, I32, I32, I32, P, P, P]),
+    'osb_conv_stem_fused_grid': (c_int, [P, I32, P, I64, P, I32, I32, I32, I32, I32, P, I32, P, P, I32, P, P, P]),
     'osb_fusion_workspace_bytes': (SZ, [I64, I32]),
     'osb_fusion_accumulate': (c_int, [P, I32, I64, P, P, P, P, I32, I32, I32, I32, I32, c_double, P, P, P, P, SZ, P]),
     'osb_fusion_finalize': (c_int, [P, P, I64, I32, P, P]),

@@ -95,6 +95,52 @@ __device__ inline int hash_lookup(const HashSlot *__restrict__ slots, uint64_t m
 }
 
 // ---------------------------------------------------------------------------------------------
+// Occupancy grid: the alternative to the hash for coordinate sets that are non-negative and fit 2^27 cells
+// (every indoor scene; the coarse levels of lidar sweeps).  One bit per cell of a 2^nbits cube per batch index, cells in
+// Morton order (x least significant), so a 64-bit word is one aligned 4x4x4 block.  Rows of a coordinate set are
+// Morton sorted, hence the rows of a word are contiguous and
+//        row(cell) = first_row[word] + popc(bits of the word below the cell).
+// A lookup is two loads from a table of a few MB that neighbouring voxels share (L1 / L2 resident) instead of a probe
+// chain of 16-byte slots scattered over a table 4x the set.
+// ---------------------------------------------------------------------------------------------
+struct OccGridView {
+  const unsigned long long *bitmap;   // [n_batch * words_per_batch]
+  const int32_t *first_row;           // [n_batch * words_per_batch], defined where bitmap != 0
+  int nbits;                          // cells per axis = 1 << nbits (2 <= nbits <= 9)
+  int log2_ts;                        // cell = coordinate >> log2_ts (coordinates of the set are multiples of the tensor stride)
+  int n_batch;
+};
+__host__ __device__ inline uint32_t spread3_10(uint32_t x) {   // 10 bits -> every third bit of 30
+  x &= 0x3FFu;
+  x = (x | (x << 16)) & 0x030000FFu;
+  x = (x | (x << 8)) & 0x0300F00Fu;
+  x = (x | (x << 4)) & 0x030C30C3u;
+  x = (x | (x << 2)) & 0x09249249u;
+  return x;
+}
+__host__ __device__ inline int64_t occgrid_words_per_batch(int nbits) { return (int64_t)1 << (3 * nbits - 6); }
+// (word, bit) of a coordinate that is known to lie inside the grid
+__device__ inline void occgrid_cell(const OccGridView &g, int b, int x, int y, int z, int64_t &word, int &bit) {
+  const uint32_t m = spread3_10((uint32_t)(x >> g.log2_ts)) | (spread3_10((uint32_t)(y >> g.log2_ts)) << 1) |
+                     (spread3_10((uint32_t)(z >> g.log2_ts)) << 2);
+  word = (int64_t)b * occgrid_words_per_batch(g.nbits) + (m >> 6);
+  bit = (int)(m & 63u);
+}
+__device__ inline int occgrid_lookup(const OccGridView &g, int b, int x, int y, int z) {
+  const uint32_t lim = 1u << g.nbits;
+  const int ts_mask = (1 << g.log2_ts) - 1;
+  // arithmetic shifts keep negatives negative -> they fail the unsigned bound test; off-lattice queries cannot match
+  if ((uint32_t)(x >> g.log2_ts) >= lim || (uint32_t)(y >> g.log2_ts) >= lim || (uint32_t)(z >> g.log2_ts) >= lim ||
+      (uint32_t)b >= (uint32_t)g.n_batch || ((x | y | z) & ts_mask))
+    return -1;
+  int64_t word; int bit;
+  occgrid_cell(g, b, x, y, z, word, bit);
+  const unsigned long long w = __ldg(g.bitmap + word);
+  if (!((w >> bit) & 1ull)) return -1;
+  return __ldg(g.first_row + word) + __popcll(w & ((1ull << bit) - 1ull));
+}
+
+// ---------------------------------------------------------------------------------------------
 // split-fp32: v ~= hi + lo, both bf16 (round-to-nearest-even).  |v - hi - lo| <= 2^-17 |v|.
 // ---------------------------------------------------------------------------------------------
 __device__ inline void split_bf16(float v, __nv_bfloat16 &hi, __nv_bfloat16 &lo) {

@@ -174,6 +174,52 @@ __global__ void k_kernel_map(const int4 *__restrict__ coords_out, int64_t n_out,
   }
 }
 
+// ---- occupancy grid (common.cuh): build + kernel map through it ----
+__global__ void k_occgrid_build(const int4 *__restrict__ coords, int64_t n, OccGridView g, unsigned long long *__restrict__ bitmap,
+                                int32_t *__restrict__ first_row, int32_t *__restrict__ status) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int4 c = coords[r];
+  const uint32_t lim = 1u << g.nbits;
+  if ((uint32_t)(c.y >> g.log2_ts) >= lim || (uint32_t)(c.z >> g.log2_ts) >= lim || (uint32_t)(c.w >> g.log2_ts) >= lim ||
+      (uint32_t)c.x >= (uint32_t)g.n_batch) {
+    atomicOr(status, 1);                                  // the caller sized the grid from the key bits: cannot happen
+    return;
+  }
+  int64_t word; int bit;
+  occgrid_cell(g, c.x, c.y, c.z, c.w, word, bit);
+  atomicOr(bitmap + word, 1ull << bit);
+  bool first = r == 0;
+  if (!first) {                                           // rows are Morton sorted: a word's rows are contiguous
+    const int4 d = coords[r - 1];
+    int64_t pw; int pb;
+    occgrid_cell(g, d.x, d.y, d.z, d.w, pw, pb);
+    first = pw != word;
+  }
+  if (first) first_row[word] = (int32_t)r;
+}
+
+__global__ void k_kernel_map_grid(const int4 *__restrict__ coords_out, int64_t n_out, OccGridView g, int ksx, int ksy, int ksz,
+                                  int step, int32_t *__restrict__ nbr, int32_t *__restrict__ pairs_per_k) {
+  const int k = blockIdx.y;
+  int ix = k % ksx, iy = (k / ksx) % ksy, iz = k / (ksx * ksy);
+  const int dx = ((ksx & 1) ? ix - ksx / 2 : ix) * step;
+  const int dy = ((ksy & 1) ? iy - ksy / 2 : iy) * step;
+  const int dz = ((ksz & 1) ? iz - ksz / 2 : iz) * step;
+  int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int hit = 0;
+  if (o < n_out) {
+    const int4 c = coords_out[o];
+    const int row = occgrid_lookup(g, c.x, c.y + dx, c.z + dy, c.w + dz);
+    nbr[(int64_t)k * n_out + o] = row;
+    hit = row >= 0;
+  }
+  if (pairs_per_k != nullptr) {
+    int cnt = __syncthreads_count(hit);
+    if (threadIdx.x == 0 && cnt) atomicAdd(pairs_per_k + k, cnt);
+  }
+}
+
 __global__ void k_fill_i32(int32_t *__restrict__ p, int64_t n, int32_t v) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -218,6 +264,15 @@ static void varying_bits(unsigned long long k_or, unsigned long long k_and, int 
 }
 
 static size_t cub_scan_bytes(int64_t n) { return scan_ws_bytes(n); }
+
+// status_host[2..5] = OR (lo, hi 32 bits) and AND (lo, hi) of the Morton keys: the caller derives from them whether all
+// coordinates are non-negative, how many bits the largest one has and the largest batch index (occupancy-grid sizing)
+static void key_bits_to_status(const unsigned long long hb[2], int32_t *status_host) {
+  status_host[2] = (int32_t)(uint32_t)(hb[0] & 0xffffffffull);
+  status_host[3] = (int32_t)(uint32_t)(hb[0] >> 32);
+  status_host[4] = (int32_t)(uint32_t)(hb[1] & 0xffffffffull);
+  status_host[5] = (int32_t)(uint32_t)(hb[1] >> 32);
+}
 
 // Sort (key, index) pairs over bits [lo, hi) such that the sorted keys land in *keys_sorted and the permutation in `perm`.
 // `k0` holds the keys (clobbered), `k1` / `v_tmp` are scratch.
@@ -301,9 +356,10 @@ int osb_coordset_build(const int32_t *coords, int64_t n, int32_t *coords_int, in
   OSB_CHECK(sort_to(morton, morton_s, idx, perm, n, lo, hi, cub_tmp, stream, &sorted_keys) == 0, "osb_coordset_build: sort failed");
   k_permute_coords<<<nb, 256, 0, stream>>>((const int4 *)coords, perm, sorted_keys, n, (int4 *)coords_int, inv_perm, status);
   OSB_LAUNCH_CHECK();
-  if (osb_hash_build(coords_int, n, slots, cap, stream_)) return 1;
+  if (slots != nullptr && osb_hash_build(coords_int, n, slots, cap, stream_)) return 1;
   OSB_CUDA(cudaMemcpyAsync(status_host, status, 8, cudaMemcpyDeviceToHost, stream));
   OSB_CUDA(cudaStreamSynchronize(stream));
+  key_bits_to_status(hb, status_host);
   return 0;
 }
 
@@ -389,7 +445,7 @@ int osb_coordset_pyramid(const int32_t *coords, int64_t n, int32_t n_levels, int
   OSB_CHECK(sort_to(morton, morton_s, idx, perm, n, lo, hi, cub_tmp, stream, &sorted_keys) == 0, "osb_coordset_pyramid: sort failed");
   k_permute_coords<<<nb, 256, 0, stream>>>((const int4 *)coords, perm, sorted_keys, n, (int4 *)coords_int, inv_perm, status);
   OSB_LAUNCH_CHECK();
-  if (osb_hash_build(coords_int, n, slots, cap, stream_)) return 1;
+  if (slots != nullptr && osb_hash_build(coords_int, n, slots, cap, stream_)) return 1;
   const int32_t *fine = coords_int;
   for (int l = 0; l < n_levels; ++l) {
     int32_t *coarse = coords_lvl + (int64_t)l * n * 4;
@@ -409,6 +465,7 @@ int osb_coordset_pyramid(const int32_t *coords, int64_t n, int32_t n_levels, int
   OSB_CUDA(cudaStreamSynchronize(stream));
   for (int l = 0; l <= n_levels; ++l) n_host[l] = hc[l];
   status_host[0] = hs[0]; status_host[1] = hs[1];
+  key_bits_to_status(hb, status_host);
   return 0;
 }
 
@@ -422,6 +479,52 @@ int osb_kernel_map_build(const int32_t *coords_out, int64_t n_out, const void *s
   dim3 grid((unsigned)ceil_div(n_out, 256), K);
   k_kernel_map<<<grid, 256, 0, stream>>>((const int4 *)coords_out, n_out, (const HashSlot *)slots_in,
                                          (uint64_t)cap_in - 1, ks_x, ks_y, ks_z, step, nbr, pairs_per_k);
+  OSB_LAUNCH_CHECK();
+  return 0;
+}
+
+static int make_grid_view(const void *grid, int32_t log2_ts, int32_t nbits, int32_t n_batch, OccGridView *g, const char *who) {
+  OSB_CHECK(grid != nullptr && nbits >= 2 && nbits <= 9 && log2_ts >= 0 && log2_ts <= 16 && n_batch >= 1 && n_batch <= 1024,
+            "%s: bad occupancy grid (nbits %d, log2_ts %d, n_batch %d)", who, nbits, log2_ts, n_batch);
+  const int64_t words = (int64_t)n_batch * occgrid_words_per_batch(nbits);
+  OSB_CHECK(words <= ((int64_t)1 << 21), "%s: occupancy grid of %lld words is too large", who, (long long)words);
+  g->bitmap = reinterpret_cast<const unsigned long long *>(grid);
+  g->first_row = reinterpret_cast<const int32_t *>(reinterpret_cast<const unsigned long long *>(grid) + words);
+  g->nbits = nbits; g->log2_ts = log2_ts; g->n_batch = n_batch;
+  return 0;
+}
+
+size_t osb_occgrid_bytes(int32_t nbits, int32_t n_batch) {
+  if (nbits < 2 || nbits > 9 || n_batch < 1) return 0;
+  const int64_t words = (int64_t)n_batch * occgrid_words_per_batch(nbits);
+  return words > ((int64_t)1 << 21) ? 0 : (size_t)words * 12;
+}
+
+int osb_occgrid_build(const int32_t *coords_int, int64_t n, int32_t log2_ts, int32_t nbits, int32_t n_batch, void *grid,
+                      int32_t *status_dev, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  OccGridView g;
+  if (make_grid_view(grid, log2_ts, nbits, n_batch, &g, "osb_occgrid_build")) return 1;
+  OSB_CHECK(n > 0 && status_dev != nullptr, "osb_occgrid_build: bad arguments");
+  const int64_t words = (int64_t)n_batch * occgrid_words_per_batch(nbits);
+  OSB_CUDA(cudaMemsetAsync(grid, 0, (size_t)words * 8, stream));          // bitmap only; first_row is read where a bit is set
+  k_occgrid_build<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>((const int4 *)coords_int, n, g, (unsigned long long *)grid,
+                                                                  const_cast<int32_t *>(g.first_row), status_dev);
+  OSB_LAUNCH_CHECK();
+  return 0;
+}
+
+int osb_kernel_map_build_grid(const int32_t *coords_out, int64_t n_out, const void *grid, int32_t log2_ts, int32_t nbits,
+                              int32_t n_batch, int32_t ks_x, int32_t ks_y, int32_t ks_z, int32_t step, int32_t *nbr,
+                              int32_t *pairs_per_k, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int K = ks_x * ks_y * ks_z;
+  OSB_CHECK(n_out > 0 && K >= 1 && K <= 1024 && step >= 1, "osb_kernel_map_build_grid: bad arguments");
+  OccGridView g;
+  if (make_grid_view(grid, log2_ts, nbits, n_batch, &g, "osb_kernel_map_build_grid")) return 1;
+  if (pairs_per_k) OSB_CUDA(cudaMemsetAsync(pairs_per_k, 0, sizeof(int32_t) * K, stream));
+  dim3 grid_dim((unsigned)ceil_div(n_out, 256), K);
+  k_kernel_map_grid<<<grid_dim, 256, 0, stream>>>((const int4 *)coords_out, n_out, g, ks_x, ks_y, ks_z, step, nbr, pairs_per_k);
   OSB_LAUNCH_CHECK();
   return 0;
 }

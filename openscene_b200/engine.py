@@ -177,15 +177,19 @@ class FusedMinkUNet:
             # above, the stem kernel sits between them and the first convolution)
             self._flags = 1 if self.use_pdl else 0
 
-            cs0 = cm.sets[1].ensure_hash()
+            cs0 = cm.sets[1].ensure_lookup()
             f32 = feats.float().contiguous()
             x_int = torch.empty_like(f32)
             C.call('osb_gather_rows_f32', C.ptr(f32), C.ptr(cm.perm), n[0], f32.shape[1], C.ptr(x_int), C.stream_ptr())
             st = self.stem
             x_a = self._cursor
             self._cursor += _al(n[0] * 4 * st.cout)
-            C.call('osb_conv_stem_fused', C.ptr(x_int), st.cin, C.ptr(cs0.coords), n[0], C.ptr(cs0.slots), cs0.cap, st.ks, 1,
-                   C.ptr(st.w3), st.cout, st.scale_a, st.shift_a, 1, x_a, None, self._stream)
+            if cs0.grid is not None:
+                C.call('osb_conv_stem_fused_grid', C.ptr(x_int), st.cin, C.ptr(cs0.coords), n[0], C.ptr(cs0.grid), *cs0.grid_args,
+                       st.ks, 1, C.ptr(st.w3), st.cout, st.scale_a, st.shift_a, 1, x_a, None, self._stream)
+            else:
+                C.call('osb_conv_stem_fused', C.ptr(x_int), st.cin, C.ptr(cs0.coords), n[0], C.ptr(cs0.slots), cs0.cap, st.ks, 1,
+                       C.ptr(st.w3), st.cout, st.scale_a, st.shift_a, 1, x_a, None, self._stream)
             skips = [(x_a, st.cout, n[0])]
             cur = skips[0]
             for l, (dconv, blocks) in enumerate(self.enc):

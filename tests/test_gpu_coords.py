@@ -153,3 +153,60 @@ def test_hand_written_sort_handles_many_tiles_and_wide_keys():
     for l, ts in ((1, 2), (2, 4)):
         exp = np.unique(np.concatenate([c[:, :1], (c[:, 1:] // ts) * ts], 1), axis=0)
         assert cm.sets[ts].n == len(exp)
+
+
+def _all_maps(cm):
+    out = {}
+    ts = 1
+    for _ in range(4):
+        new = cm.stride(ts, 2)
+        out[(ts, new, 2)] = cm.kernel_map(ts, new, 2)
+        out[(ts, ts, 3)] = cm.kernel_map(ts, ts, 3)
+        ts = new
+    out[(ts, ts, 3)] = cm.kernel_map(ts, ts, 3)
+    out[(1, 1, 5)] = cm.kernel_map(1, 1, 5)
+    out[(1, 1, 3, 2)] = cm.kernel_map(1, 1, 3, dilation=2)
+    return out
+
+
+@pytest.mark.parametrize('case', ['room', 'batch3', 'wide', 'negative', 'single'])
+@pytest.mark.parametrize('pyramid', [0, 4])
+def test_occupancy_grid_maps_equal_hash_maps(case, pyramid, monkeypatch):
+    """The occupancy-grid lookup (csrc/common.cuh) and the hash table must give identical kernel maps; sets that the grid
+    cannot represent (negative coordinates, > 2^9 cells per axis) fall back to the hash per level."""
+    from openscene_b200.coords import CoordinateManager
+    if case == 'room':
+        c = synth.scene('tiny')
+    elif case == 'batch3':
+        c = synth.random_cloud(3000, 45, seed=5, batch=3)
+    elif case == 'wide':                    # 3000 cells per axis: levels 0-2 on the hash, 3-4 on the grid
+        c = synth.random_cloud(6000, 3000, seed=6)
+        c = np.concatenate([c, c + np.array([0, 1, 0, 0], dtype=np.int32), c + np.array([0, 0, 2, 1], dtype=np.int32)])
+        c = np.unique(c, axis=0).astype(np.int32)
+    elif case == 'negative':
+        c = synth.random_cloud(2000, 30, seed=7)
+        c[:, 1:] -= 9
+    else:                                   # nearly dense 4^3 block at the origin: the smallest grid (one word)
+        c = synth.random_cloud(60, 4, seed=8)
+    ct = torch.from_numpy(c).to(_dev())
+    monkeypatch.setenv('OSB_OCCGRID', '1')
+    cm_g = CoordinateManager(ct, pyramid_levels=pyramid)
+    maps_g = _all_maps(cm_g)
+    monkeypatch.setenv('OSB_OCCGRID', '0')
+    cm_h = CoordinateManager(ct, pyramid_levels=pyramid)
+    maps_h = _all_maps(cm_h)
+    assert all(s.grid is None for s in cm_h.sets.values())
+    used = {ts: s.grid is not None for ts, s in cm_g.sets.items()}
+    if case in ('room', 'batch3', 'single'):
+        assert all(used.values())
+    elif case == 'wide':
+        assert used == {1: False, 2: False, 4: False, 8: True, 16: True}
+    else:
+        assert not any(used.values())
+    if cm_g.grid_status is not None:
+        assert int(cm_g.grid_status.item()) == 0
+    for key in maps_h:
+        assert torch.equal(cm_g.sets[key[0]].coords, cm_h.sets[key[0]].coords)
+        assert torch.equal(maps_g[key].nbr, maps_h[key].nbr), key
+        assert torch.equal(maps_g[key].pairs_per_k, maps_h[key].pairs_per_k), key
+        assert maps_g[key].num_pairs() > 0

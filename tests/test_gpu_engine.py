@@ -85,3 +85,18 @@ def test_steady_state_makes_no_device_allocations():
         assert torch.cuda.memory_reserved() == reserved
     finally:
         gc.enable()
+
+
+def test_occupancy_grid_and_hash_engines_are_bit_identical(monkeypatch):
+    """Stem probes and kernel maps through the occupancy grid or the hash table: same maps, same accumulation order."""
+    from openscene_b200 import engine
+    c = synth.scene('config1_50k')
+    f = torch.rand(len(c), 3, generator=torch.Generator().manual_seed(5))
+    model = synth.build_model('MinkUNet18A', 96, seed=1).eval().to(DEV)
+    eng = engine.FusedMinkUNet(model)
+    outs = {}
+    for flag in ('1', '0'):
+        monkeypatch.setenv('OSB_OCCGRID', flag)
+        outs[flag] = eng(torch.from_numpy(c).to(DEV), f.to(DEV)).clone()
+        assert (eng.last_cm.sets[1].grid is not None) == (flag == '1')
+    assert torch.equal(outs['1'], outs['0'])
