@@ -8,11 +8,14 @@ convolution:
 * BatchNorm (eval) is folded into the producing convolution's epilogue (scale/shift), ReLU and the
   BasicBlock residual add likewise; ``ME.cat`` is never materialised (the next convolution reads two
   sources); activations stay in the split-bf16 layout between layers;
-* the 5x5x5 stem fuses its 125-offset hash probe with the 3->32 FMA (no 5^3 kernel map in HBM);
+* the 5x5x5 stem fuses its 125 neighbour lookups (occupancy grid, or the hash where that does not fit) with the 3->32 FMA
+  (no 5^3 kernel map in HBM);
 * the final 1x1x1 convolution writes fp32 rows straight into the caller's row order.
 
 Results equal the module-by-module path within the bf16x3 tolerance (tests/test_gpu_engine.py).
 """
+import os
+
 import torch
 
 from . import _cabi as C
@@ -59,7 +62,6 @@ class FusedMinkUNet:
         if net.training:
             raise RuntimeError("FusedMinkUNet folds BatchNorm running statistics: call model.eval() first")
         self.device = p.device
-        import os
         self.dense_up = os.environ.get('OSB_DENSE_UP', '1') != '0'
         with torch.cuda.device(self.device), torch.no_grad():
             self.stem = _Conv(net.conv0p1s1, net.bn0, keep_f32=True)
@@ -83,7 +85,6 @@ class FusedMinkUNet:
         self.last_cm = None
         self._ws = None
         self._arena = None
-        import os
         self.use_pdl = os.environ.get('OSB_PDL', '1') != '0'
         self.use_pyramid = os.environ.get('OSB_PYRAMID', '1') != '0'
         if 'OSB_TC_LAZY' in os.environ:                      # tuning: 0 = smem index prologue, 1 = lazy on >= 2-wave launches, 2 = always
