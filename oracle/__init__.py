@@ -21,4 +21,9 @@ Parity status ("Oracle"):
   the golden activations were produced by running the reference's unmodified
   ``models/mink_unet.py`` on top of ``me_cpu``.
 * ``matching``      -- restates ``run/evaluate.py:283-326`` and ``run/distill.py:322-328``.
+* ``fusion_ref``    -- restates ``PointCloudToImageMapper.compute_mapping`` (PINNED to the reference's own outputs,
+  ``tests/golden/fusion_mapping_*.npz``) and the accumulate loop of ``scripts/feature_fusion/scannet_openseg.py``.
+* ``loader_ref``    -- restates the fused-feature remap of ``dataset/feature_loader.py:101-172`` (PINNED to the
+  outputs of the reference's own ``FusedFeatureLoader``, ``tests/golden/loader_*.npz``).
+* ``metric_ref``    -- restates ``util/metric.py`` and ``util/util.py:117-145`` (PINNED, ``tests/golden/metric_*.npz``).
 """
