@@ -109,8 +109,13 @@ def _stub_modules(*names):
 def golden_fusion():
     _stub_modules('tensorflow', 'tensorflow.io', 'tensorflow.compat', 'tensorflow.compat.v1')
     sys.path.insert(0, os.path.join(REF, 'scripts', 'feature_fusion'))
-    from fusion_util import PointCloudToImageMapper
+    from fusion_util import PointCloudToImageMapper, adjust_intrinsic, make_intrinsic
     from openscene_b200.synth import fusion_case
+    # the intrinsics helpers with the ScanNet / Matterport-style numbers the fusion scripts use (scannet_openseg.py:124-160)
+    k0 = make_intrinsic(fx=577.870605, fy=577.870605, mx=319.5, my=239.5)
+    k1 = adjust_intrinsic(k0.copy(), intrinsic_image_dim=[640, 480], image_dim=(320, 240))
+    k2 = adjust_intrinsic(make_intrinsic(1075.1, 1075.8, 629.7, 522.3), intrinsic_image_dim=[1280, 1024], image_dim=(640, 512))
+    np.savez_compressed(os.path.join(OUT, 'fusion_intrinsics.npz'), k0=k0, k1=k1, k2=k2)
     cases = {'depth_cut10': dict(seed=21, n=6000, with_depth=True, cut=10),
              'depth_cut0': dict(seed=22, n=5000, with_depth=True, cut=0),
              'nodepth_cut5': dict(seed=23, n=5000, with_depth=False, cut=5)}

@@ -65,3 +65,15 @@ def test_loader_remap_restatement_matches_reference(case):
     assert feat.dtype == torch.float16 and np.array_equal(feat.numpy(), g['feat_3d'])
     if 'inds_reverse' in g.files:
         assert np.array_equal(inv, g['inds_reverse'])
+
+
+def test_intrinsics_helpers_match_reference():
+    """make_intrinsic / adjust_intrinsic (host-side NumPy in openscene_b200/fusion.py) against fusion_util.py:17-39."""
+    from openscene_b200.fusion import adjust_intrinsic, make_intrinsic
+    g = golden('fusion_intrinsics.npz')
+    k0 = make_intrinsic(fx=577.870605, fy=577.870605, mx=319.5, my=239.5)
+    assert np.array_equal(k0, g['k0'])
+    assert np.array_equal(adjust_intrinsic(k0.copy(), [640, 480], (320, 240)), g['k1'])
+    assert np.array_equal(adjust_intrinsic(make_intrinsic(1075.1, 1075.8, 629.7, 522.3), [1280, 1024], (640, 512)), g['k2'])
+    same = make_intrinsic(1.0, 2.0, 3.0, 4.0)
+    assert adjust_intrinsic(same, [320, 240], [320, 240]) is same
