@@ -133,6 +133,12 @@ def golden_metric():
     sys.path.insert(0, REF)
     from util import metric as ref_metric
     from util import util as ref_util
+    from dataset import label_constants as lc
+    # class counts evaluate() derives from the dataset name (util/metric.py:47-60)
+    np.savez_compressed(os.path.join(OUT, 'metric_class_counts.npz'), names=np.array(['scannet_3d', 'matterport_3d_40', 'matterport_3d_80',
+                        'matterport_3d_160', 'matterport_3d', 'nuscenes_3d']),
+                        counts=np.array([len(lc.SCANNET_LABELS_20), len(lc.MATTERPORT_LABELS_40), len(lc.MATTERPORT_LABELS_80),
+                                         len(lc.MATTERPORT_LABELS_160), len(lc.MATTERPORT_LABELS_21), len(lc.NUSCENES_LABELS_16)]))
     orig_cuda = torch.Tensor.cuda
     torch.Tensor.cuda = lambda self, *a, **k: self
     try:

@@ -77,3 +77,12 @@ def test_intrinsics_helpers_match_reference():
     assert np.array_equal(adjust_intrinsic(make_intrinsic(1075.1, 1075.8, 629.7, 522.3), [1280, 1024], (640, 512)), g['k2'])
     same = make_intrinsic(1.0, 2.0, 3.0, 4.0)
     assert adjust_intrinsic(same, [320, 240], [320, 240]) is same
+
+
+def test_dataset_class_counts_match_reference_label_lists():
+    """evaluate() picks the class count from the dataset name (util/metric.py:47-60, dataset/label_constants.py)."""
+    from openscene_b200.metric import _DATASET_CLASSES
+    g = golden('metric_class_counts.npz')
+    for name, count in zip(g['names'].tolist(), g['counts'].tolist()):
+        picked = next(n for key, n in _DATASET_CLASSES if key in name)       # first match wins, as the reference's elif chain
+        assert picked == count, (name, picked, count)
