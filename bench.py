@@ -372,6 +372,17 @@ def main():
                                 'launches_per_step': conv_calls, 'kernel_ms_per_step': conv_ms,
                                 'algorithmic_bytes_per_step': conv_bytes, 'tflops': conv_flops / (conv_ms * 1e-3) / 1e12,
                                 'step_algorithmic_bytes': all_bytes, 'step_gflop': all_flops / 1e9}
+            try:      # second lens: bf16 MMA work behind the algorithmic fp32 flops (3 passes per product) vs the measured bf16 peak
+                pk = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))).get('bf16_tflops')
+                if pk:
+                    tf3 = 3.0 * line['roofline']['tflops']
+                    line['roofline']['tensor_lens'] = {
+                        'bf16_tflops': tf3, 'peak': float(pk), 'frac': tf3 / float(pk),
+                        'note': 'algorithmic pairs x 3 bf16 passes; the 128-row tiles also multiply the zero rows of missing '
+                                'neighbours (about half of the rows at level 0), so the tensor pipe itself is ~2x busier: 52% '
+                                'active on the level-0 layers (profiles/r01_ncu_full_conv_tc_96x96_k3_final.md)'}
+            except Exception:
+                pass
         if world == 1 and not args.no_cpu_baseline:
             sample = crop_sample(coords_np, 25_000)
             threads = host_threads()
