@@ -98,7 +98,9 @@ class FeatureFusion:
         self.sum_features = torch.zeros((n, feat_dim), dtype=torch.float32, device=mapper.device)
         self.counter = torch.zeros(n, dtype=torch.float32, device=mapper.device)
 
-    def add_frames(self, poses, depths, feats, intrinsics=None):
+    def add_frames(self, poses, depths, feats, intrinsics=None, channels_first=None):
+        """feats: fp16 [F,H,W,C], or the reference's permuted [F,C,H,W] view (``channels_first=True``; None = detect from
+        the shape, which is ambiguous only when the image width equals the feature width)."""
         dev = self.mapper.device
         W, H = self.mapper.image_dim
         if isinstance(feats, (list, tuple)):
@@ -107,7 +109,9 @@ class FeatureFusion:
         if feats.dtype != torch.float16:
             feats = feats.half()
         F = feats.shape[0]
-        if feats.shape[1] == self.feat_dim and feats.shape[-1] != self.feat_dim:
+        if channels_first is None:
+            channels_first = feats.shape[1] == self.feat_dim and feats.shape[-1] != self.feat_dim
+        if channels_first:
             feats = feats.permute(0, 2, 3, 1)                    # the reference's [C,H,W] view of HWC memory
         feats = feats.contiguous()
         assert feats.shape == (F, H, W, self.feat_dim), f"features must be [F,{H},{W},{self.feat_dim}]"
