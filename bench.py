@@ -123,13 +123,13 @@ def crop_sample(coords, target):
 
 def cpu_pass(coords, arch, k_text, threads):
     """One pass of the CPU restatement (oracle/) over `coords`: map building + forward + cosine matching."""
-    from openscene_b200 import minkunet, synth
+    from openscene_b200 import synth
     from oracle import matching as om
     from oracle import me_cpu
     torch.set_num_threads(threads)
     model = cpu_pass.cache.get(arch)
     if model is None:
-        model = synth.build_model(arch, 768, seed=0, ME=minkunet.oracle_me()).eval()
+        model = synth.build_model(arch, 768, seed=0, ME=me_cpu.as_module()).eval()
         cpu_pass.cache[arch] = model
     text = torch.from_numpy(synth.text_embeddings(k_text))
     feats = torch.ones(len(coords), 3)
@@ -156,34 +156,47 @@ def host_threads():
     return max(1, min(n, int(os.environ.get('OSB_CPU_THREADS', 16))))
 
 
+def workload_config(args, n_vox):
+    """The `config` object, identical in both arms (the driver compares them)."""
+    return {'workload': f'{args.workload}: {n_vox} voxels/scene, one scene per GPU, {args.arch}, 768-d head, '
+                        f'K_text={args.k_text}, cosine (L2-normalised) scores + argmax',
+            'points': 'stride-1 voxels fed to SparseTensor',
+            'l2': 'GPU arm: L2 flushed (256 MiB memset) before every timed step; CPU arm: working set (~2 GB of activations) '
+                  'far beyond the last-level cache'}
+
+
 def run_reference(args, rank):
     """`--impl reference`: the reference's CPU path for this metric.  MinkowskiEngine itself is not installable
-    offline, so this times oracle/ -- the PyTorch-CPU restatement of the same algorithm -- on a bounded
-    sample per step, all host threads."""
+    offline, so this times oracle/ -- the PyTorch-CPU restatement of the same algorithm -- on the SAME
+    scene as the GPU arm (the full workload; ~5 s per step for config2_200k on 16 host threads).  Only if the whole
+    `--steps K --warmup W` run would exceed ~6 minutes is the per-step sample cut to an x-slab of the scene, and the line
+    then says so (`same_config: false`)."""
     if rank != 0:
         return
     from openscene_b200 import synth
-    scene = synth.scene(args.workload)
-    coords = crop_sample(scene, 25_000)
+    scene = synth.scene(args.workload, seed=0)
+    coords = scene
     threads = host_threads()
-    # keep the whole run (warm-up + timed steps) near two minutes whatever K and W the caller asks for: probe one pass,
-    # then shrink the per-step sample (an x-slab of the same scene) if needed
-    t_probe = cpu_pass(coords, args.arch, args.k_text, threads)
-    budget_s, total = 120.0, args.steps + args.warmup
+    t_probe = cpu_pass(coords, args.arch, args.k_text, threads)          # first pass: also the first warm-up
+    budget_s, total = 360.0, args.steps + max(args.warmup, 1)
     if t_probe * total > budget_s:
         coords = crop_sample(scene, max(4000, int(len(coords) * budget_s / (t_probe * total))))
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup - 1, 1 if coords is not scene else 0)):
         cpu_pass(coords, args.arch, args.k_text, threads)
     ts = [cpu_pass(coords, args.arch, args.k_text, threads) for _ in range(args.steps)]
     tot = sum(ts)
     value = len(coords) * args.steps / tot
+    full = len(coords) == len(scene)
     line = {'impl': 'reference', 'metric': 'voxels/s MinkUNet34C fwd + 768-d cosine-sim', 'value': value, 'unit': 'voxels/s',
             'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * tot / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': f'{args.workload} ({args.arch}, 768-d head, K_text={args.k_text})',
-                       'note': 'CPU restatement of gather-GEMM-scatter (oracle/), not MinkowskiEngine itself'},
+            'config': workload_config(args, len(scene)), 'same_config': full,
+            'voxels_per_step': len(coords), 'voxels_per_step_gpu_arm': len(scene),
             'cpu_baseline': {'value': value, 'unit': 'voxels/s', 'cores': threads, 'kind': 'port',
-                             'sample': f'x-slab crop of {args.workload}: {len(coords)} voxels per step'},
+                             'sample': (f'the full {args.workload} scene, {len(coords)} voxels per step' if full else
+                                        f'x-slab crop of {args.workload}: {len(coords)} of {len(scene)} voxels per step '
+                                        f'(a full-scene step takes {t_probe:.1f} s)'),
+                             'note': 'PyTorch-CPU restatement of gather-GEMM-scatter (oracle/), not MinkowskiEngine itself'},
             'e2e': {'value': value, 'unit': 'voxels/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line))
@@ -348,10 +361,7 @@ def main():
             'unit': 'voxels/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': t_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'bf16x3 (split fp32 operands, fp32 accumulate)', 'data': 'synthetic',
-            'config': {'workload': f'{args.workload}: {n0} voxels/scene, one scene per GPU, {args.arch}, 768-d head, '
-                                   f'K_text={args.k_text}, cosine (L2-normalised) scores + argmax',
-                       'path': 'module surface' if args.modules else 'fused engine', 'l2': 'flushed (256 MiB memset) before every timed step',
-                       'points': 'stride-1 voxels fed to SparseTensor'},
+            'config': workload_config(args, n0), 'path': 'module surface' if args.modules else 'fused engine',
             'e2e': {'value': total_vox * args.steps / (t_e2e / 1e3), 'unit': 'voxels/s', 'ms_per_step': t_e2e / args.steps,
                     'h2d_bytes_per_step': int(coords_host.numel() * 4 + feats_host.numel() * 4), 'd2h_bytes_per_step': int(n0 * 8)},
             'gpu_launches': int(launches), 'clocks': clocks, 'step_ms_stats': step_stats,
@@ -384,11 +394,11 @@ def main():
             except Exception:
                 pass
         if world == 1 and not args.no_cpu_baseline:
-            sample = crop_sample(coords_np, 25_000)
             threads = host_threads()
-            dt = cpu_pass(sample, args.arch, args.k_text, threads)
-            line['cpu_baseline'] = {'value': len(sample) / dt, 'unit': 'voxels/s', 'cores': threads, 'kind': 'port',
-                                    'sample': f'x-slab crop of the same scene: {len(sample)} voxels, one pass, {dt:.1f} s',
+            cpu_pass(coords_np, args.arch, args.k_text, threads)                   # warm-up pass (allocator, thread pool)
+            dt = cpu_pass(coords_np, args.arch, args.k_text, threads)
+            line['cpu_baseline'] = {'value': n0 / dt, 'unit': 'voxels/s', 'cores': threads, 'kind': 'port',
+                                    'sample': f'the full scene of this run ({n0} voxels): one warm-up pass + one timed pass of {dt:.1f} s',
                                     'note': 'PyTorch-CPU restatement of gather-GEMM-scatter (oracle/), not MinkowskiEngine'}
         print(json.dumps(line))
     if world > 1:

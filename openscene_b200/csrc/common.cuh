@@ -41,6 +41,28 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE property of a kernel: remember it per device (a process
+// may drive several GPUs, and autograd's backward thread calls in from another host thread).  Setting it twice is harmless.
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> done{0};
+  bool need(int *dev_out) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    *dev_out = dev;
+    return dev < 0 || dev >= 64 || !((done.load(std::memory_order_acquire) >> dev) & 1ull);
+  }
+  void mark(int dev) { if (dev >= 0 && dev < 64) done.fetch_or(1ull << dev, std::memory_order_release); }
+};
+#define OSB_SMEM_ATTR_ONCE(kernel, bytes)                                                              \
+  do {                                                                                                 \
+    static ::osb::PerDeviceOnce _once;                                                                 \
+    int _dev;                                                                                          \
+    if (_once.need(&_dev)) {                                                                           \
+      OSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+      _once.mark(_dev);                                                                                \
+    }                                                                                                  \
+  } while (0)
+
 // ---------------------------------------------------------------------------------------------
 // Coordinate keys.  Fields: x,y,z biased by 2^17 into 18 bits each, batch in the top 10 bits.
 //   pack   = b<<54 | z<<36 | y<<18 | x        (hash key; neighbour = one 64-bit add)

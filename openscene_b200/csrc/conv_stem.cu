@@ -132,11 +132,7 @@ int osb_conv_stem_fused(const float *in, int32_t cin, const int32_t *coords, int
   size_t smem = 0;
   if (stem_check(cin, cout, ks, out_split, scale, shift, n, &smem)) return 1;
   OSB_CHECK(slots != nullptr && cap > 0 && (cap & (cap - 1)) == 0, "osb_conv_stem_fused: bad hash table");
-  static bool configured = false;
-  if (!configured) {
-    OSB_CUDA(cudaFuncSetAttribute(k_conv_stem<StemHashLookup>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
-  }
+  OSB_SMEM_ATTR_ONCE(k_conv_stem<StemHashLookup>, 200 * 1024);
   const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(n, STEM_WARPS), 148 * 3);
   const StemHashLookup lk{(const HashSlot *)slots, (uint64_t)cap - 1};
   k_conv_stem<StemHashLookup><<<grid, STEM_WARPS * 32, smem, stream>>>(in, cin, (const int4 *)coords, n, lk, ks, step, w, cout, scale,
@@ -155,11 +151,7 @@ int osb_conv_stem_fused_grid(const float *in, int32_t cin, const int32_t *coords
                 (int64_t)n_batch * occgrid_words_per_batch(nbits) <= ((int64_t)1 << 21),
             "osb_conv_stem_fused_grid: bad occupancy grid (nbits %d, log2_ts %d, n_batch %d)", nbits, log2_ts, n_batch);
   OSB_CHECK(ks * step < (1 << 16), "osb_conv_stem_fused_grid: offsets too large");
-  static bool configured = false;
-  if (!configured) {
-    OSB_CUDA(cudaFuncSetAttribute(k_conv_stem<StemGridLookup>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
-  }
+  OSB_SMEM_ATTR_ONCE(k_conv_stem<StemGridLookup>, 200 * 1024);
   const int64_t words = (int64_t)n_batch * occgrid_words_per_batch(nbits);
   StemGridLookup lk;
   lk.g.bitmap = reinterpret_cast<const unsigned long long *>(grid_);

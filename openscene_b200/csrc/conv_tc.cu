@@ -704,11 +704,7 @@ static int conv_fwd_tc_impl(const void *src0, int32_t c0, int64_t n_src0, const 
     p.partial = (float *)ws;
   }
 
-  static size_t configured = 0;
-  if (smem_bytes > configured) {
-    OSB_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = 227 * 1024;
-  }
+  OSB_SMEM_ATTR_ONCE(k_conv_tc, 227 * 1024);
   dim3 grid((unsigned)ceil_div(n_out, TC_M), (unsigned)(cp / p.nt), (unsigned)p.nsplit);
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

@@ -231,12 +231,10 @@ static int launch_match_tc(const MatchTcParams &p, const void *text_f16, cudaStr
   const size_t smem = (size_t)NP * MT_M * 128 + MT_BSTAGES * MT_NW * 128 + 128 + 1024;
   const unsigned grid = (unsigned)ceil_div(p.n_pts, MT_M);
   if (NP == 12) {
-    static bool cfg = false;
-    if (!cfg) { OSB_CUDA(cudaFuncSetAttribute(k_match_tc<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); cfg = true; }
+    OSB_SMEM_ATTR_ONCE(k_match_tc<12>, 227 * 1024);
     k_match_tc<12><<<grid, MT_THREADS, smem, stream>>>(tmT, p);
   } else {
-    static bool cfg = false;
-    if (!cfg) { OSB_CUDA(cudaFuncSetAttribute(k_match_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); cfg = true; }
+    OSB_SMEM_ATTR_ONCE(k_match_tc<8>, 227 * 1024);
     k_match_tc<8><<<grid, MT_THREADS, smem, stream>>>(tmT, p);
   }
   OSB_LAUNCH_CHECK();

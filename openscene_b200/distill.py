@@ -3,6 +3,7 @@
 One process per GPU, scenes sharded by rank (``DistributedSampler`` semantics, run/distill.py:183-184), plain
 per-rank BatchNorm (the reference never enables SyncBN, run/distill.py:108), gradient all-reduce through
 ``DistributedDataParallel`` over NCCL, three small metric all-reduces in validation (run/distill.py:429-431)."""
+import math
 import os
 
 import torch
@@ -27,7 +28,9 @@ def shard_indices(n_items, rank, world, epoch=0, shuffle=True, seed=0):
     else:
         order = list(range(n_items))
     per = (n_items + world - 1) // world
-    order += order[:per * world - n_items]
+    pad = per * world - n_items
+    if pad > 0:                                   # DistributedSampler: repeat the list when pad > len (n_items < world / 2)
+        order += (order * math.ceil(pad / len(order)))[:pad]
     return order[rank:per * world:world]
 
 

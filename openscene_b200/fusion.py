@@ -66,10 +66,12 @@ class PointCloudToImageMapper:
         self.intrinsics = intrinsics
         self.device = torch.device(device)
 
-    def compute_mapping(self, camera_to_world, coords, depth=None, intrinsic=None):
-        """Returns a CUDA int32 tensor [N,3] = (row, col, visible) -- the values of the reference's NumPy result."""
+    def compute_mapping(self, camera_to_world, coords, depth=None, intrinsic=None, as_tensor=False):
+        """[N,3] = (row, col, visible).  Default: a NumPy int array, exactly what the reference returns (its caller writes
+        it into a NumPy buffer, scannet_openseg.py:95); ``as_tensor=True`` keeps the CUDA int32 tensor on the device."""
         if self.intrinsics is not None:
             intrinsic = self.intrinsics
+        assert intrinsic is not None, "PointCloudToImageMapper: no intrinsics given (constructor or compute_mapping argument)"
         pts = _dev_points(coords, self.device)
         W, H = self.image_dim
         with torch.cuda.device(self.device):
@@ -79,7 +81,7 @@ class PointCloudToImageMapper:
                 d = torch.as_tensor(depth).to(self.device, torch.float64).contiguous().view(1, H, W)
             out = torch.empty((1, pts.shape[0], 3), dtype=torch.int32, device=self.device)
             _launch(pts, w2c, k, d, None, 1, H, W, 8, self.cut_bound, self.vis_thres, None, None, out)
-        return out[0]
+        return out[0] if as_tensor else out[0].cpu().numpy().astype(int)
 
 
 class FeatureFusion:
@@ -117,6 +119,7 @@ class FeatureFusion:
         assert feats.shape == (F, H, W, self.feat_dim), f"features must be [F,{H},{W},{self.feat_dim}]"
         assert len(poses) == F
         if intrinsics is None:
+            assert self.mapper.intrinsics is not None, "FeatureFusion.add_frames: no intrinsics (mapper has none, none passed)"
             intrinsics = [self.mapper.intrinsics] * F
         if depths is not None and any(d is None for d in depths):
             assert all(d is None for d in depths), "either every frame of a batch has a depth image or none"

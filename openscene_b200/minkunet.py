@@ -41,13 +41,6 @@ def default_me():
     return ns
 
 
-def oracle_me():
-    """Namespace over the CPU oracle (tests / cpu_baseline only)."""
-    from oracle import me_cpu
-    ns = types.SimpleNamespace(**{k: getattr(me_cpu, k) for k in dir(me_cpu) if not k.startswith('_')})
-    return ns
-
-
 class MinkUNet(nn.Module):
     def __init__(self, arch='MinkUNet18A', in_channels=3, out_channels=20, D=3, ME=None):
         super().__init__()

@@ -352,6 +352,13 @@ def kaiming_normal_(tensor, a=0, mode='fan_in', nonlinearity='leaky_relu'):
         return tensor.normal_(0, std)
 
 
+def as_module():
+    """This oracle as the ``ME`` namespace argument of ``openscene_b200.minkunet.mink_unet`` / ``synth.build_model``
+    (tests, smoke() and bench.py's CPU arm only)."""
+    me = sys.modules[__name__]
+    return types.SimpleNamespace(**{k: getattr(me, k) for k in dir(me) if not k.startswith('_')})
+
+
 def install_as_minkowski_engine():
     """Register this oracle as ``MinkowskiEngine`` in sys.modules so that the reference's
     unmodified ``models/*.py`` can be imported on top of it (golden generation only)."""

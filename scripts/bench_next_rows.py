@@ -49,7 +49,7 @@ def bench_fusion(n=1_000_000, c=768, F=32):
     fuser.add_frames(poses, list(d_dev), feats)
     launches = C.lib().osb_launch_count() - l0
     ms = timed(lambda: fuser.add_frames(poses, list(d_dev), feats))
-    maps = torch.stack([mapper.compute_mapping(p, pts, d) for p, d in zip(poses, depths)])
+    maps = torch.stack([mapper.compute_mapping(p, pts, d, as_tensor=True) for p, d in zip(poses, depths)])
     vis = maps[:, :, 2].long()
     pairs, touched = int(vis.sum()), int((vis.sum(0) > 0).sum())
     # algorithmic bytes: points once per frame (24 B), depth probe (8 B) per in-image pair ~ per pair, the pixel feature

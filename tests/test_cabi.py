@@ -45,8 +45,4 @@ def test_product_never_imports_oracle():
                 if fn.endswith('.py'):
                     src = open(os.path.join(dp, fn)).read()
                     hits = [m for m in pat.finditer(src)]
-                    # the only sanctioned use: minkunet.oracle_me(), a test helper that imports lazily
-                    if fn == 'minkunet.py':
-                        assert len(hits) == 1 and 'def oracle_me' in src
-                    else:
-                        assert not hits, f"{pkg}/{fn} imports the oracle"
+                    assert not hits, f"{pkg}/{fn} imports the oracle"

@@ -65,5 +65,16 @@ def test_shard_indices_matches_distributed_sampler():
         assert list(iter(s)) == distill.shard_indices(11, rank, 4, epoch=2, shuffle=True, seed=5)
 
 
+def test_shard_indices_with_fewer_items_than_half_the_ranks():
+    """3 scenes on 8 ranks: the padded list must repeat (every rank gets one index, or DDP's all-reduce deadlocks)."""
+    from torch.utils.data.distributed import DistributedSampler
+    ds = list(range(3))
+    for rank in range(8):
+        s = DistributedSampler(ds, num_replicas=8, rank=rank, shuffle=True, seed=1)
+        s.set_epoch(4)
+        got = distill.shard_indices(3, rank, 8, epoch=4, shuffle=True, seed=1)
+        assert len(got) == 1 and got == list(iter(s))
+
+
 def test_poly_lr():
     assert abs(distill.poly_learning_rate(1e-4, 50, 100) - 1e-4 * 0.5 ** 0.9) < 1e-12

@@ -21,14 +21,18 @@ def test_mapping_matches_reference_vectors(case):
     pts, poses, depths, intr = fusion_case(int(g['seed']), int(g['n']), bool(g['with_depth']))
     mapper = PointCloudToImageMapper(image_dim=IMG, intrinsics=intr, visibility_threshold=0.25, cut_bound=int(g['cut']), device=DEV)
     for f, (pose, depth) in enumerate(zip(poses, depths)):
-        m = mapper.compute_mapping(pose, pts, depth)
+        m = mapper.compute_mapping(pose, pts, depth, as_tensor=True)
         assert m.dtype == torch.int32 and m.shape == (len(pts), 3)
         assert np.array_equal(m.cpu().numpy(), g['mapping'][f])
+        mn = mapper.compute_mapping(pose, pts, depth)                    # default: NumPy int array like the reference
+        assert isinstance(mn, np.ndarray) and mn.dtype == np.zeros(1, dtype=int).dtype and np.array_equal(mn, g['mapping'][f])
+        buf = np.zeros((len(pts), 4), dtype=int)
+        buf[:, 1:4] = mn                                                 # the reference's own use (scannet_openseg.py:95)
     # float32 points are promoted to float64 exactly as np.concatenate([coords, ones]) does
     m32 = mapper.compute_mapping(poses[0], pts.astype(np.float32), depths[0])
     from oracle import fusion_ref
     want = fusion_ref.compute_mapping(poses[0], pts.astype(np.float32), depths[0], intr, IMG, int(g['cut']))
-    assert np.array_equal(m32.cpu().numpy(), want)
+    assert np.array_equal(m32, want)
 
 
 @pytest.mark.parametrize('n,c,n_frames,image_dim,with_depth,seed', [
@@ -127,7 +131,7 @@ def test_fusion_fullsize_properties():
     fuser = FeatureFusion(pts, c, mapper)
     fuser.add_frames(poses, depths, feats)
     bank, ids = fuser.finalize()
-    maps = torch.stack([mapper.compute_mapping(p, pts, d) for p, d in zip(poses, depths)]).long()     # [F,N,3]
+    maps = torch.stack([mapper.compute_mapping(p, pts, d, as_tensor=True) for p, d in zip(poses, depths)]).long()     # [F,N,3]
     vis = maps[:, :, 2]
     assert torch.equal(fuser.counter, vis.sum(0).float())
     assert torch.equal(ids, torch.nonzero(vis.sum(0) > 0)[:, 0])

@@ -41,7 +41,7 @@ def test_train_mode_batchnorm_and_backward_match_oracle():
     c = synth.scene('tiny')
     f = torch.rand(len(c), 3, generator=torch.Generator().manual_seed(0))
     tgt = torch.randn(len(c), 64, generator=torch.Generator().manual_seed(1))
-    m64 = synth.build_model('MinkUNet14A', 64, seed=0, ME=minkunet.oracle_me()).double().train()
+    m64 = synth.build_model('MinkUNet14A', 64, seed=0, ME=me_cpu.as_module()).double().train()
     mpt = copy.deepcopy(m64)
     g = torch.Generator().manual_seed(5)
     with torch.no_grad():

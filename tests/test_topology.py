@@ -13,7 +13,7 @@ from tests.util import golden, rel_row_err
 @pytest.mark.parametrize('arch', ['MinkUNet18A', 'MinkUNet34C'])
 def test_mirror_reproduces_reference_model(arch):
     g = golden(f'unet_{arch}.npz')
-    model = synth.build_model(arch, 768, seed=0, ME=minkunet.oracle_me()).double().eval()
+    model = synth.build_model(arch, 768, seed=0, ME=me_cpu.as_module()).double().eval()
     sd = model.state_dict()
     assert list(sd.keys()) == g['state_keys'].tolist()
     assert [str(tuple(v.shape)) for v in sd.values()] == g['state_shapes'].tolist()
@@ -43,6 +43,6 @@ def test_expected_checkpoint_key_names():
 def test_disnet_prefix():
     import types
     cfg = types.SimpleNamespace(arch_3d='MinkUNet14A', feature_2d_extractor='lseg')
-    net = minkunet.DisNet(cfg, ME=minkunet.oracle_me())
+    net = minkunet.DisNet(cfg, ME=me_cpu.as_module())
     assert all(k.startswith('net3d.') for k in net.state_dict())
     assert net.net3d.final.kernel.shape == (96, 512)
