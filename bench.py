@@ -316,7 +316,7 @@ def main():
     conv_ms, conv_calls = 0.0, 0
     if not args.modules:
         pend = []
-        hooked_names = ('osb_conv_fwd_tc', 'osb_convtr_fwd_tc')          # every launch of k_conv_tc goes through these two
+        hooked_names = ('osb_conv_fwd_tc', 'osb_convtr_fwd_tc', 'osb_conv_chain_launch')   # every tensor-core convolution launch
 
         def make_hook(real_fn):
             def hooked(*a):

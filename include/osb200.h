@@ -11,8 +11,9 @@
  *   osb_conv_*                          `MinkowskiConvolution.forward` / `MinkowskiConvolutionTranspose.forward`
  *        (gather -> GEMM -> scatter-add per sparse-conv layer; models/mink_unet.py:116-174) and their autograd
  *        backward (run/distill.py:333).
- *   osb_bn_* / osb_relu_* ...           `MinkowskiBatchNorm` / `MinkowskiReLU` on the [N,C] feature matrix
- *        (models/mink_unet.py:50,114).
+ *        `MinkowskiBatchNorm` (eval) / `MinkowskiReLU` / the BasicBlock residual / `ME.cat` have no entry points of their
+ *        own: they are arguments of osb_conv_* (scale/shift, relu, res, src1), folded into the convolution's epilogue
+ *        (models/mink_unet.py:50,114,147).
  *   osb_match_*                         `predictions[inds_reverse]`, `x/(|x|+1e-5)`, `.half() @ text_features.t()`,
  *        `torch.max(pred,1)` (run/evaluate.py:288-323).
  *   osb_voxelize_*                      `Voxelizer.voxelize` + `sparse_quantize`/`fnv_hash_vec`
@@ -30,7 +31,8 @@
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
  *     unless documented ("SYNC");
  *   - the CALLER allocates every output and workspace (sizes via the *_workspace_bytes queries), so
- *     memory stays in the caller's allocator; the library keeps no per-call state;
+ *     memory stays in the caller's allocator; the library keeps no per-call state (the only process-wide state are the
+ *     tuning knobs of osb_tuning_set, which never change results);
  *   - every function returns 0 on success, non-zero on failure; osb_last_error() returns a
  *     thread-local description; no exception crosses the ABI;
  *   - there is no CPU fallback: on a machine without an sm_100 GPU every compute entry point fails.
@@ -169,6 +171,41 @@ int osb_conv_fwd_tc(const void *src0, int32_t c0, int64_t n_src0, const void *sr
 int osb_convtr_fwd_tc(const void *src, int32_t cin, int64_t n_coarse, const int32_t *down_nbr, int32_t kvol, const void *wpack,
                       int32_t cout, const float *scale, const float *shift, int32_t relu, void *out_split, float *out_f32,
                       int32_t flags, void *stream);
+
+
+/* ----------------------------------------------------------- persistent convolution chains (conv_chain.cu)
+ * Second-generation tensor-core path: ONE launch executes a list of convolution layers (`MinkowskiConvolution` /
+ * `MinkowskiConvolutionTranspose` forwards of consecutive modules of models/mink_unet.py:116-174, BasicBlock included) with
+ * one persistent CTA per SM, dedicated epilogue warps, a double-buffered TMEM accumulator, split-K reduced inside the
+ * kernel and grid barriers between dependent layers.  Same arithmetic and the same argument meaning as osb_conv_fwd_tc.
+ *
+ * A layer is described by an opaque record of osb_conv_desc_bytes() bytes, filled on the HOST by osb_conv_desc_fill and
+ * copied by the caller into device memory (descs_dev) before osb_conv_chain_launch; the launch also reads the host copy.
+ *   wtiles          osb_conv_pack_weight_tiles(w [K,cin,cout]) -- tile-major, pre-swizzled B operands
+ *   cmap/cmap_cout  non-NULL: dense transposed stride-2 convolution as in osb_convtr_fwd_tc (wtiles of the [1,cin,kvol*cout]
+ *                   matrix, cout = kvol*cmap_cout, cmap = the stride-2 map [kvol, n_out] of the matching strided conv)
+ *   ws / ws_bytes   scratch for split-K partials, osb_conv_chain_workspace_bytes(...) bytes (0 = not split).  Consecutive
+ *                   split layers without a barrier between them need different scratch
+ *   barrier_before  != 0: this layer reads (src*, res) what an earlier layer of the SAME launch wrote
+ *   grid_barrier    2 x uint32 in device memory, zeroed once when allocated (never reset afterwards); required when any
+ *                   layer of the launch is split or asks for a barrier.  One launch at a time may use it.
+ *   flags           bit0: PDL, as in osb_conv_fwd_tc */
+size_t osb_conv_desc_bytes(void);
+size_t osb_conv_weight_tiles_bytes(int32_t K, int32_t cin, int32_t cout);
+int osb_conv_pack_weight_tiles(const float *w, int32_t K, int32_t cin, int32_t cout, int32_t transpose_w, void *wtiles,
+                               void *stream);
+int osb_conv_chain_grid(void);
+size_t osb_conv_chain_workspace_bytes(int64_t n_out, int32_t K, int32_t cin, int32_t cout);
+int osb_conv_desc_fill(void *desc_host, const void *src0, int32_t c0, const void *src1, int32_t c1, const int32_t *nbr,
+                       int64_t n_out, int32_t K, const void *wtiles, int32_t cout, const float *scale, const float *shift,
+                       const void *res, int32_t relu, void *out_split, float *out_f32, const int32_t *out_row_map,
+                       const int32_t *cmap, int32_t cmap_cout, void *ws, size_t ws_bytes, int32_t barrier_before);
+int osb_conv_chain_launch(const void *descs_dev, const void *descs_host, int32_t n_layers, void *grid_barrier,
+                          int32_t flags, void *stream);
+
+/* Process-wide tuning knobs (tile shapes, ring depths, split factors, profiling hooks).  They select between
+ * equivalent schedules and never change results; unknown names fail.  Names: see csrc/conv_chain.cu, csrc/conv_tc.cu. */
+int osb_tuning_set(const char *name, int64_t value);
 
 /* Stem: fused kernel-map probe + conv for tiny cin (<= 3) and cout <= 32, fp32 FMA.  One launch replaces the
  * 5x5x5 map build (125 probes / voxel) and the 3->32 convolution of `conv0p1s1`.

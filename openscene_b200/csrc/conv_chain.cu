@@ -1,0 +1,630 @@
+// Persistent, plan-driven sparse convolution on 5th-gen tensor cores (second generation of conv_tc.cu).
+//
+//   out[o,:] = epilogue( sum_k  in[nbr[k][o], :] @ W[k] )         (output-stationary, no atomics)
+//
+// One launch executes a LIST of convolution layers ("chain") described by ConvDesc records in device memory.  The grid
+// is one CTA per SM; every CTA owns a contiguous range of each layer's work units (unit = 128 output rows x one N tile x
+// one split of the (offset, channel-block) stage sequence) and walks it with warp-specialised roles that never leave
+// their loops between units:
+//
+//   warp 0      weight tiles: one cp.async.bulk per stage from the tile-major, pre-swizzled packing (no tensor map)
+//   warp 1      TMEM owner + single-thread tcgen05.mma issuer
+//   warps 4-7   gathered A rows: cp.async 16 B x 8 lanes per 128-byte row line, hand-applied 128B swizzle, the kernel
+//               map read per offset straight from global memory, one offset ahead
+//   warps 8-15  two epilogue groups, one per TMEM accumulator buffer: TMEM -> registers -> BN affine / residual / ReLU ->
+//               swizzled staging tile -> full-line coalesced stores (split rows, fp32 rows, or raw split-K partials)
+//
+// What changed against conv_tc.cu, and why (profiles/r01_ncu_full_conv_tc_96x96_k3_final.md, DESIGN.md "slot model"):
+//   * separate rings for gathered rows and weight tiles; the whole SM's shared memory belongs to one CTA: 9-10 row
+//     slots of 16 KB in flight per SM instead of 6 (the stage rate was latency x row bytes in flight);
+//   * two 128-row sub-tiles share every weight tile (256 output rows per item): half the L2->SM weight stream;
+//   * the accumulator is double buffered in TMEM (2 x 256 columns) and drained by dedicated epilogue warps while the
+//     next item's MMAs run; barrier / TMEM set-up is paid once per CTA, not once per tile; work is split evenly over
+//     the SMs (no 6-vs-5.2 wave tail);
+//   * split-K partials are reduced INSIDE the kernel after a grid barrier, and consecutive small layers (levels 2-4 of
+//     the U-Net) run in one launch with grid barriers between dependent layers: no launch / finish-kernel boundaries.
+//
+// Numerics are those of conv_tc.cu: split-bf16 operands (v = hi + lo), hi*Whi + hi*Wlo + lo*Whi on kind::f16 MMAs,
+// fp32 accumulation in TMEM, deterministic (fixed-order) split-K reduction.
+#include "tc_ptx.cuh"
+#include <algorithm>
+#include <cstring>
+#include <string>
+
+namespace osb {
+
+constexpr int CH_THREADS = 512;
+constexpr int CH_M = 128;                        // rows per sub-tile (UMMA M)
+constexpr int CH_A_BYTES = CH_M * 128;           // one row slot: 128 rows x one 32-channel block
+constexpr int CH_STG_BYTES = 8 * 4096;           // epilogue staging: 8 warps x (32 rows x 128 B)
+constexpr int CH_SS_FLOATS = 768;                // folded BN constants kept in shared memory per layer (scale | shift)
+constexpr int CH_MAX_SA = 12, CH_MAX_SB = 4;
+constexpr int CH_DESC_WORDS = 48;                // sizeof(ConvDesc) / 4
+
+struct __align__(16) ConvDesc {
+  const uint8_t *src0, *src1;      // split rows of the (up to) two sources ([src0 | src1] = ME.cat)
+  const int32_t *nbr;              // [K][n_out] input row per (offset, output row), -1 = none; NULL = identity (K == 1)
+  const uint8_t *wtiles;           // tile-major pre-swizzled weights (osb_conv_pack_weight_tiles)
+  const float *scale, *shift;      // folded BatchNorm, or NULL
+  const uint8_t *res;              // residual split rows [n_out, cout], or NULL
+  uint8_t *out_split;              // split rows out, or NULL
+  float *out_f32;                  // fp32 rows out, or NULL
+  const int32_t *out_row_map;      // fp32 rows scattered: row o -> out_row_map[o]
+  const int32_t *cmap;             // dense transposed conv: column block kch of row o -> fine row cmap[kch*n_out + o]
+  float *partial;                  // [nsplit][n_out][cout_pad] raw accumulators (nsplit > 1)
+  int64_t n_out;
+  int K, nb0, nb1;
+  int cout, cout_pad, nt, n_ntiles;
+  int relu, cmap_cout, nsplit, m_tiles;
+  int nsub_max;                    // sub-tiles per item that may share a weight tile: 2 when nt <= 128, else 1
+  int barrier_before;              // grid barrier before this layer (it reads what an earlier layer of the launch wrote)
+  int stages_per_split;            // ceil(K * (nb0 + nb1) / nsplit)
+  int pad[8];
+};
+static_assert(sizeof(ConvDesc) == CH_DESC_WORDS * 4, "ConvDesc layout");
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Sense-reversing grid barrier over {count, generation} in global memory (both zero before the first use ever; the
+// barrier leaves count == 0 behind, so no host-side reset between launches).  Every CTA of the grid must be resident:
+// the launch uses at most one CTA per SM.
+__device__ __forceinline__ void grid_barrier(unsigned *gbar, unsigned &gen) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned old = atomicAdd(gbar, 1u);
+    if (old == gridDim.x - 1) {
+      gbar[0] = 0;
+      __threadfence();
+      atomicAdd(gbar + 1, 1u);
+    } else {
+      unsigned it = 0;
+      while (ld_acquire_u32(gbar + 1) == gen) {
+        if (++it > (1u << 24)) __trap();          // a CTA that never arrives must not hang the GPU
+      }
+    }
+    __threadfence();
+  }
+  gen += 1;
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(CH_THREADS, 1)
+k_conv_chain(const ConvDesc *__restrict__ descs, int n_layers, unsigned *gbar, int sa, int sb, int bslot, int flags,
+             long long *dbg_clock) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t *smem_b = smem + sa * CH_A_BYTES;                                  // weight ring (1024-aligned slots)
+  uint8_t *stg = smem_b + sb * bslot;                                        // epilogue staging
+  float *s_ss = reinterpret_cast<float *>(stg + CH_STG_BYTES);               // [scale x CH_SS_FLOATS | shift x CH_SS_FLOATS]
+  ConvDesc *s_desc = reinterpret_cast<ConvDesc *>(s_ss + 2 * CH_SS_FLOATS);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(s_desc) + 256);
+  uint32_t *s_misc = reinterpret_cast<uint32_t *>(bars + 40);                // [0] TMEM base
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (flags & 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (dbg_clock && tid == 0) dbg_clock[blockIdx.x * 8 + 0] = clock64();
+  const uint32_t fullA = smem_u32(bars), emptyA = smem_u32(bars + 12);
+  const uint32_t fullB = smem_u32(bars + 24), emptyB = smem_u32(bars + 28);
+  const uint32_t accFull = smem_u32(bars + 32), accEmpty = smem_u32(bars + 34);
+
+  if (tid == 0) {
+    for (int s = 0; s < sa; ++s) { mbar_init(fullA + 8 * s, 128); mbar_init(emptyA + 8 * s, 1); }
+    for (int s = 0; s < sb; ++s) { mbar_init(fullB + 8 * s, 1); mbar_init(emptyB + 8 * s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(accFull + 8 * b, 1); mbar_init(accEmpty + 8 * b, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // all 512 TMEM columns: two accumulator buffers of 256 columns (one CTA per SM, no contention)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_misc[0])), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  unsigned bar_gen = 0;
+  if (tid == 0 && gbar) bar_gen = ld_acquire_u32(gbar + 1);    // before this launch's first barrier can complete
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  // Everything above touched no data of an earlier kernel in the stream; from here on we read activations.
+  if (flags & 1) asm volatile("griddepcontrol.wait;" ::: "memory");
+  const uint32_t tmem_base = s_misc[0];
+  if (dbg_clock && tid == 0) dbg_clock[blockIdx.x * 8 + 1] = clock64();
+
+  // pipeline state of this thread's role; persists over items and layers
+  uint32_t a_slot = 0, a_phase = 0, b_slot = 0, b_phase = 0, n_item = 0;
+
+  for (int L = 0; L < n_layers; ++L) {
+    __syncthreads();                                   // every role is done with the previous layer (and with s_desc)
+    if (tid < CH_DESC_WORDS) reinterpret_cast<uint32_t *>(s_desc)[tid] = __ldg(reinterpret_cast<const uint32_t *>(descs + L) + tid);
+    __syncthreads();
+    const ConvDesc &d = *s_desc;
+    {                                                  // folded BN constants of the layer -> shared memory
+      const int nss = d.cmap ? d.cmap_cout : d.cout;
+      for (int c = tid; c < nss && c < CH_SS_FLOATS; c += CH_THREADS) {
+        s_ss[c] = d.scale ? __ldg(d.scale + c) : 1.f;
+        s_ss[CH_SS_FLOATS + c] = d.shift ? __ldg(d.shift + c) : 0.f;
+      }
+    }
+    if (d.barrier_before) {
+      grid_barrier(gbar, bar_gen);                     // (only thread 0's copy of bar_gen is meaningful)
+    } else {
+      __syncthreads();
+    }
+
+    const int nb = d.nb0 + d.nb1;
+    const int T = d.K * nb;                                            // stages of one full (offset, channel block) sweep
+    const int64_t U = (int64_t)d.m_tiles * d.n_ntiles * d.nsplit;      // work units of the layer
+    const int64_t u_begin = U * blockIdx.x / gridDim.x, u_end = U * (blockIdx.x + 1) / gridDim.x;
+    const int64_t per_z = (int64_t)d.m_tiles * d.n_ntiles;
+    const uint32_t b_bytes = (uint32_t)d.nt * 128u;
+
+    // item = 1 or 2 consecutive units (same split, same N tile, adjacent row tiles) sharing every weight tile
+#define CH_FOR_ITEMS()                                                                                         \
+    for (int64_t u = u_begin, _n; u < u_end; u += _n)                                                          \
+      if (const int z = (int)(u / per_z), r_ = (int)(u - (int64_t)z * per_z), nti = r_ / d.m_tiles,            \
+          m = r_ - nti * d.m_tiles, nsub = (d.nsub_max == 2 && u + 1 < u_end && m + 1 < d.m_tiles) ? 2 : 1,    \
+          t_begin = min(z * d.stages_per_split, T), t_end = min(t_begin + d.stages_per_split, T);              \
+          (_n = nsub, true))
+
+    if (warp == 0) {
+      // ============================ weight tiles ====================================
+      CH_FOR_ITEMS() {
+        (void)m;
+        for (int t = t_begin; t < t_end; ++t) {
+          mbar_wait(emptyB + 8 * b_slot, b_phase ^ 1);
+          if (elect_one()) {
+            const uint32_t fb = fullB + 8 * b_slot;
+            mbar_expect_tx(fb, b_bytes);
+            bulk_g2s(smem_u32(smem_b + b_slot * bslot), d.wtiles + ((int64_t)t * d.n_ntiles + nti) * b_bytes, b_bytes, fb);
+          }
+          __syncwarp();
+          if (++b_slot == (uint32_t)sb) { b_slot = 0; b_phase ^= 1; }
+        }
+      }
+    } else if (warp == 1) {
+      // ================================ MMA issuer ===================================
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(d.nt >> 3) << 17) | ((uint32_t)(CH_M >> 4) << 24);
+      CH_FOR_ITEMS() {
+        (void)m; (void)nti;
+        const uint32_t buf = n_item & 1u;
+        mbar_wait(accEmpty + 8 * buf, ((n_item >> 1) & 1u) ^ 1u);         // the epilogue drained this buffer
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int t = t_begin; t < t_end; ++t) {
+          mbar_wait(fullB + 8 * b_slot, b_phase);
+          const uint64_t db = umma_desc(smem_u32(smem_b + b_slot * bslot));
+          for (int s = 0; s < nsub; ++s) {
+            mbar_wait(fullA + 8 * a_slot, a_phase);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) writes -> UMMA reads
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+              const uint64_t da = umma_desc(smem_u32(smem + a_slot * CH_A_BYTES));
+              const uint32_t dcol = tmem_base + buf * 256u + (uint32_t)s * 128u;
+              // 128-byte line = [hi ch0-15 | hi ch16-31 | lo ch0-15 | lo ch16-31]; +2 per 32-byte K slice
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                umma_bf16(dcol, da + 2 * h, db + 2 * h, idesc, (h == 0 && t == t_begin) ? 0u : 1u);   // hi * Whi
+                umma_bf16(dcol, da + 2 * h, db + 2 * h + 4, idesc, 1u);                                // hi * Wlo
+                umma_bf16(dcol, da + 2 * h + 4, db + 2 * h, idesc, 1u);                                // lo * Whi
+              }
+              umma_commit(emptyA + 8 * a_slot);                             // row slot free when these MMAs retire
+            }
+            __syncwarp();
+            if (++a_slot == (uint32_t)sa) { a_slot = 0; a_phase ^= 1; }
+          }
+          if (elect_one()) umma_commit(emptyB + 8 * b_slot);
+          __syncwarp();
+          if (++b_slot == (uint32_t)sb) { b_slot = 0; b_phase ^= 1; }
+        }
+        if (elect_one()) umma_commit(accFull + 8 * buf);
+        __syncwarp();
+        ++n_item;
+      }
+    } else if (warp >= 4 && warp < 8) {
+      // ================= gathered A rows: 32 rows of each slot per warp ====================
+      // 8 lanes cover one 128-byte row line (one L2 line), 4 rows per warp instruction, 8 instructions per slot;
+      // the destination carries the 128B swizzle (chunk ^ (row & 7)); a missing neighbour is a zero-fill copy.
+      const int w = warp - 4, j = lane & 7, q = lane >> 3;
+      CH_FOR_ITEMS() {
+        (void)nti;
+        const int64_t row0 = (int64_t)m * CH_M;
+        int32_t cur[2][8], nxt[2][8];
+        auto fetch = [&](int k, int32_t (&r)[2][8]) {
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int64_t o = row0 + s * CH_M + w * 32 + 4 * i + q;
+              r[s][i] = (s < nsub && o < d.n_out) ? (d.nbr ? __ldg(d.nbr + (int64_t)k * d.n_out + o) : (int32_t)o) : -1;
+            }
+          }
+        };
+        int k_cur = t_begin / nb;
+        if (t_begin < t_end) fetch(k_cur, nxt);
+        for (int t = t_begin; t < t_end;) {
+#pragma unroll
+          for (int s = 0; s < 2; ++s)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cur[s][i] = nxt[s][i];
+          const int t_next_k = min((k_cur + 1) * nb, t_end);                // first stage of the next offset
+          if (t_next_k < t_end) fetch(k_cur + 1, nxt);                      // one offset ahead: latency behind this offset's copies
+          for (; t < t_next_k; ++t) {
+            const int cb = t - k_cur * nb;
+            const bool first = cb < d.nb0;
+            const uint8_t *src = first ? d.src0 : d.src1;
+            const int64_t row_bytes = (int64_t)(first ? d.nb0 : d.nb1) * 128;
+            const int col_byte = (first ? cb : cb - d.nb0) * 128 + j * 16;
+            for (int s = 0; s < nsub; ++s) {
+              mbar_wait(emptyA + 8 * a_slot, a_phase ^ 1);
+              const uint32_t a_dst = smem_u32(smem + a_slot * CH_A_BYTES) + (w * 32 + q) * 128;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int m7 = (4 * i + q) & 7;
+                const int32_t r = (s == 0) ? cur[0][i] : cur[1][i];
+                const bool valid = r >= 0;
+                const uint8_t *sp = valid ? src + (int64_t)r * row_bytes + col_byte : src;
+                cp_async16(a_dst + i * 512 + ((j ^ m7) << 4), sp, valid ? 16u : 0u);      // size 0 -> zero fill
+              }
+              cp_async_arrive_noinc(fullA + 8 * a_slot);
+              if (++a_slot == (uint32_t)sa) { a_slot = 0; a_phase ^= 1; }
+            }
+          }
+          ++k_cur;
+        }
+      }
+    } else if (warp >= 8) {
+      // ================= epilogue: group g drains accumulator buffer g ====================
+      const int eg = (warp - 8) >> 2;                 // epilogue group = accumulator buffer
+      const int q = warp & 3;                         // TMEM lane quarter this warp may access
+      const uint32_t stgw = smem_u32(stg) + (uint32_t)(warp - 8) * 4096u;
+      const int rsub = lane >> 3, chunk = lane & 7, sw = lane & 7;
+      const uint32_t my_line = stgw + lane * 128;
+      auto lds128 = [](uint32_t a) { uint4 v; asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; };
+      auto sts128 = [](uint32_t a, uint4 v) { asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); };
+      CH_FOR_ITEMS() {
+        if ((n_item & 1u) != (uint32_t)eg) { ++n_item; continue; }
+        mbar_wait(accFull + 8 * eg, (n_item >> 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int s = 0; s < nsub; ++s) {
+          const int64_t wrow0 = (int64_t)(m + s) * CH_M + q * 32;        // first global row of this warp
+          const int64_t o = wrow0 + lane;
+          int32_t my_orow = (int32_t)min(o, d.n_out - 1);
+          if (d.out_row_map && o < d.n_out) my_orow = __ldg(d.out_row_map + o);
+          // staged tile (32 rows x 128 B, swizzled) -> global, 4 full lines per instruction
+          auto flush_tile = [&](uint8_t *base, int64_t row_bytes, int64_t col_byte, bool mapped) {
+            uint4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = 4 * i + rsub;
+              v[i] = lds128(stgw + r * 128 + ((chunk ^ (r & 7)) << 4));
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = 4 * i + rsub;
+              const int32_t mo = __shfl_sync(0xffffffffu, my_orow, r);
+              const int64_t grow = mapped ? (int64_t)mo : wrow0 + r;
+              if (wrow0 + r < d.n_out && grow >= 0)
+                *reinterpret_cast<uint4 *>(base + grow * row_bytes + col_byte + chunk * 16) = v[i];
+            }
+          };
+          for (int cbo = 0; cbo < d.nt / 32; ++cbo) {
+            float y[32];
+            {
+              uint32_t v0[16], v1[16];
+              const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)eg * 256u + (uint32_t)s * 128u + cbo * 32;
+              tmem_ld16(taddr, v0);
+              tmem_ld16(taddr + 16, v1);
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+              for (int jj = 0; jj < 16; ++jj) { y[jj] = __uint_as_float(v0[jj]); y[16 + jj] = __uint_as_float(v1[jj]); }
+            }
+            const int c0 = nti * d.nt + cbo * 32;             // first output channel of this 32-block
+            if (d.nsplit > 1) {                               // raw partial sums; the reduce phase applies the epilogue
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                sts128(my_line + ((g ^ sw) << 4), make_uint4(__float_as_uint(y[4 * g]), __float_as_uint(y[4 * g + 1]),
+                                                             __float_as_uint(y[4 * g + 2]), __float_as_uint(y[4 * g + 3])));
+              __syncwarp();
+              flush_tile(reinterpret_cast<uint8_t *>(d.partial + (int64_t)z * d.n_out * d.cout_pad), (int64_t)d.cout_pad * 4,
+                         (int64_t)c0 * 4, false);
+              __syncwarp();
+              continue;
+            }
+            if (c0 >= d.cout) continue;                       // warp-uniform (padding columns)
+            int oc0 = c0, out_c = d.cout, kch = 0;
+            if (d.cmap) {                                     // dense transposed conv: this column block belongs to child kch
+              kch = c0 / d.cmap_cout;
+              oc0 = c0 - kch * d.cmap_cout;
+              out_c = d.cmap_cout;
+              my_orow = (o < d.n_out) ? __ldg(d.cmap + (int64_t)kch * d.n_out + o) : -1;
+            }
+            if (d.scale != nullptr) {
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj) y[jj] = fmaf(y[jj], s_ss[oc0 + jj], s_ss[CH_SS_FLOATS + oc0 + jj]);
+            }
+            if (d.res) {                                      // residual tile: coalesced load -> staging -> own row
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int r = 4 * i + rsub;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (wrow0 + r < d.n_out)
+                  v = __ldcg(reinterpret_cast<const uint4 *>(d.res + (wrow0 + r) * (int64_t)d.cout * 4 + (c0 >> 5) * 128 + chunk * 16));
+                sts128(stgw + r * 128 + ((chunk ^ (r & 7)) << 4), v);
+              }
+              __syncwarp();
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const uint4 hq = lds128(my_line + ((g ^ sw) << 4)), lq = lds128(my_line + (((4 + g) ^ sw) << 4));
+                const __nv_bfloat16 *hh = reinterpret_cast<const __nv_bfloat16 *>(&hq);
+                const __nv_bfloat16 *ll = reinterpret_cast<const __nv_bfloat16 *>(&lq);
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) y[g * 8 + jj] += join_bf16(hh[jj], ll[jj]);
+              }
+              __syncwarp();
+            }
+            if (d.relu) {
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj) y[jj] = fmaxf(y[jj], 0.f);
+            }
+            if (d.out_split) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                __align__(16) __nv_bfloat16 hh[8], ll[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) split_bf16(y[g * 8 + jj], hh[jj], ll[jj]);
+                sts128(my_line + ((g ^ sw) << 4), *reinterpret_cast<const uint4 *>(hh));
+                sts128(my_line + (((4 + g) ^ sw) << 4), *reinterpret_cast<const uint4 *>(ll));
+              }
+              __syncwarp();
+              flush_tile(d.out_split, (int64_t)out_c * 4, (int64_t)(oc0 >> 5) * 128, d.cmap != nullptr);
+              __syncwarp();
+            }
+            if (d.out_f32) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                sts128(my_line + ((g ^ sw) << 4), make_uint4(__float_as_uint(y[4 * g]), __float_as_uint(y[4 * g + 1]),
+                                                             __float_as_uint(y[4 * g + 2]), __float_as_uint(y[4 * g + 3])));
+              __syncwarp();
+              flush_tile(reinterpret_cast<uint8_t *>(d.out_f32), (int64_t)out_c * 4, (int64_t)oc0 * 4,
+                         d.out_row_map != nullptr || d.cmap != nullptr);
+              __syncwarp();
+            }
+          }
+        }
+        // this warp's TMEM reads of the buffer are complete (tcgen05.wait::ld above): hand it back to the MMA warp
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(accEmpty + 8 * eg);
+        ++n_item;
+      }
+    }
+#undef CH_FOR_ITEMS
+
+    if (d.nsplit > 1) {
+      // ---- split-K: every partial is in global memory after this barrier; reduce + epilogue by all threads of the grid
+      grid_barrier(gbar, bar_gen);
+      const int groups = d.cout / 8;
+      const int64_t total = d.n_out * groups;
+      for (int64_t e = (int64_t)blockIdx.x * CH_THREADS + tid; e < total; e += (int64_t)gridDim.x * CH_THREADS) {
+        const int64_t o = e / groups;
+        const int c0 = (int)(e - o * groups) * 8;
+        float y[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int z = 0; z < d.nsplit; ++z) {
+          const float4 *pp = reinterpret_cast<const float4 *>(d.partial + ((int64_t)z * d.n_out + o) * d.cout_pad + c0);
+          const float4 a = __ldcg(pp), b = __ldcg(pp + 1);
+          y[0] += a.x; y[1] += a.y; y[2] += a.z; y[3] += a.w; y[4] += b.x; y[5] += b.y; y[6] += b.z; y[7] += b.w;
+        }
+        if (d.scale) {
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) y[jj] = fmaf(y[jj], s_ss[c0 + jj], s_ss[CH_SS_FLOATS + c0 + jj]);
+        }
+        const int64_t off = o * (int64_t)d.cout * 4 + split_off_hi(c0);
+        if (d.res) {
+          const uint4 hq = __ldcg(reinterpret_cast<const uint4 *>(d.res + off)), lq = __ldcg(reinterpret_cast<const uint4 *>(d.res + off + 64));
+          const __nv_bfloat16 *hh = reinterpret_cast<const __nv_bfloat16 *>(&hq);
+          const __nv_bfloat16 *ll = reinterpret_cast<const __nv_bfloat16 *>(&lq);
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) y[jj] += join_bf16(hh[jj], ll[jj]);
+        }
+        if (d.relu) {
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) y[jj] = fmaxf(y[jj], 0.f);
+        }
+        if (d.out_split) {
+          __align__(16) __nv_bfloat16 hh[8], ll[8];
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) split_bf16(y[jj], hh[jj], ll[jj]);
+          *reinterpret_cast<uint4 *>(d.out_split + off) = *reinterpret_cast<const uint4 *>(hh);
+          *reinterpret_cast<uint4 *>(d.out_split + off + 64) = *reinterpret_cast<const uint4 *>(ll);
+        }
+        if (d.out_f32) {
+          const int64_t orow = d.out_row_map ? (int64_t)__ldg(d.out_row_map + o) : o;
+          float4 *op = reinterpret_cast<float4 *>(d.out_f32 + orow * d.cout + c0);
+          op[0] = make_float4(y[0], y[1], y[2], y[3]);
+          op[1] = make_float4(y[4], y[5], y[6], y[7]);
+        }
+      }
+    }
+  }
+
+  if (dbg_clock && tid == 0) dbg_clock[blockIdx.x * 8 + 2] = clock64();
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+}
+
+// ------------------------------------------------------------ tile-major, pre-swizzled weight packing
+// wtiles[((k*nb + cb) * n_ntiles + nti)] = nt rows (output channels) x 128 B, each row the split line
+// [hi ch0-15 | hi ch16-31 | lo ch0-15 | lo ch16-31] of input channels [32cb, 32cb+32), with the 16-byte chunks of row n
+// stored at chunk ^ (n & 7): exactly what a 128B-swizzled TMA tile load would leave in shared memory, so that one
+// linear cp.async.bulk per stage fetches a ready-to-multiply B operand (no tensor map, nothing to encode per launch).
+__global__ void k_pack_weight_tiles(const float *__restrict__ w, int K, int cin, int cout, int cout_pad, int nt, int transpose_w,
+                                    uint8_t *__restrict__ wt) {
+  const int nb = cin / 32, n_ntiles = cout_pad / nt;
+  const int64_t total = (int64_t)K * cout_pad * cin;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % cin);
+    const int64_t kn = e / cin;
+    const int ng = (int)(kn % cout_pad), k = (int)(kn / cout_pad);
+    float v = 0.f;
+    if (ng < cout) v = transpose_w ? w[((int64_t)k * cout + ng) * cin + c] : w[((int64_t)k * cin + c) * cout + ng];
+    __nv_bfloat16 hi, lo;
+    split_bf16(v, hi, lo);
+    const int cb = c >> 5, ci = c & 31, nti = ng / nt, n = ng - nti * nt;
+    uint8_t *tile = wt + ((((int64_t)k * nb + cb) * n_ntiles) + nti) * (int64_t)nt * 128;
+    const int jh = ci >> 3, el = ci & 7;
+    *reinterpret_cast<__nv_bfloat16 *>(tile + n * 128 + (((jh) ^ (n & 7)) << 4) + el * 2) = hi;
+    *reinterpret_cast<__nv_bfloat16 *>(tile + n * 128 + (((4 + jh) ^ (n & 7)) << 4) + el * 2) = lo;
+  }
+}
+
+}  // namespace osb
+
+namespace osb { bool conv_tc_tuning(const char *name, int64_t v); }
+using namespace osb;
+
+static inline int chain_cout_pad(int cout) { return cout <= 256 ? (cout + 15) / 16 * 16 : (cout + 255) / 256 * 256; }
+static inline int chain_nt(int cout) { const int cp = chain_cout_pad(cout); return cp <= 256 ? cp : 256; }
+
+extern "C" {
+
+size_t osb_conv_desc_bytes(void) { return sizeof(ConvDesc); }
+
+size_t osb_conv_weight_tiles_bytes(int32_t K, int32_t cin, int32_t cout) { return (size_t)K * chain_cout_pad(cout) * cin * 4; }
+
+int osb_conv_pack_weight_tiles(const float *w, int32_t K, int32_t cin, int32_t cout, int32_t transpose_w, void *wtiles, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  OSB_CHECK(K >= 1 && cin % 32 == 0 && cin > 0 && cout > 0, "osb_conv_pack_weight_tiles: cin (%d) must be a multiple of 32", cin);
+  const int cp = chain_cout_pad(cout), nt = chain_nt(cout);
+  const int64_t total = (int64_t)K * cp * cin;
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(total, 256), 148 * 32);
+  k_pack_weight_tiles<<<grid, 256, 0, stream>>>(w, K, cin, cout, cp, nt, transpose_w, (uint8_t *)wtiles);
+  OSB_LAUNCH_CHECK();
+  return 0;
+}
+
+// Split factor and scratch of one layer when it runs on a grid of `grid_ctas` CTAs.
+static int chain_nsplit(int64_t n_out, int K, int cin, int cout, int grid_ctas, int force) {
+  const int cp = chain_cout_pad(cout), nt = chain_nt(cout);
+  const int64_t tiles = ceil_div(n_out, CH_M) * (cp / nt);
+  int nsplit = force > 0 ? force : (int)(grid_ctas / tiles);
+  return std::max(1, std::min(nsplit, std::min(32, K * (cin / 32))));
+}
+
+static int g_chain_force_split = 0;      // tuning: > 0 forces the split factor of every layer (1 disables splitting)
+static int g_chain_nsub = 2;             // tuning: 1 = never pair sub-tiles
+static int g_chain_grid = 0;             // tuning: CTAs per launch (0 = one per SM)
+static int g_chain_sa = 0, g_chain_sb = 0;   // tuning: ring depths (0 = as many row slots as fit / 3 or 2 weight slots)
+static long long *g_chain_dbg_clock = nullptr;
+
+int osb_tuning_set(const char *name, int64_t value) {
+  const std::string n(name ? name : "");
+  if (n == "chain_force_split") g_chain_force_split = (int)value;
+  else if (n == "chain_nsub") g_chain_nsub = (int)value;
+  else if (n == "chain_grid") g_chain_grid = (int)value;
+  else if (n == "chain_sa") g_chain_sa = (int)value;
+  else if (n == "chain_sb") g_chain_sb = (int)value;
+  else if (n == "chain_dbg_clock") g_chain_dbg_clock = (long long *)(intptr_t)value;
+  else { OSB_CHECK(conv_tc_tuning(n.c_str(), value), "osb_tuning_set: unknown knob '%s'", n.c_str()); }
+  return 0;
+}
+
+int osb_conv_chain_grid(void) {
+  if (g_chain_grid > 0) return g_chain_grid;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
+size_t osb_conv_chain_workspace_bytes(int64_t n_out, int32_t K, int32_t cin, int32_t cout) {
+  const int ns = chain_nsplit(n_out, K, cin, cout, osb_conv_chain_grid(), g_chain_force_split);
+  return ns > 1 ? (size_t)ns * n_out * chain_cout_pad(cout) * sizeof(float) : 0;
+}
+
+int osb_conv_desc_fill(void *desc_host, const void *src0, int32_t c0, const void *src1, int32_t c1, const int32_t *nbr, int64_t n_out,
+                       int32_t K, const void *wtiles, int32_t cout, const float *scale, const float *shift, const void *res,
+                       int32_t relu, void *out_split, float *out_f32, const int32_t *out_row_map, const int32_t *cmap,
+                       int32_t cmap_cout, void *ws, size_t ws_bytes, int32_t barrier_before) {
+  OSB_CHECK(desc_host != nullptr, "osb_conv_desc_fill: no descriptor");
+  OSB_CHECK(src0 && c0 > 0 && c0 % 32 == 0 && c1 >= 0 && c1 % 32 == 0, "osb_conv_desc_fill: channel counts must be multiples of 32 (c0=%d c1=%d)", c0, c1);
+  OSB_CHECK((c1 == 0) == (src1 == nullptr), "osb_conv_desc_fill: src1 / c1 mismatch");
+  OSB_CHECK(K >= 1 && K <= 32, "osb_conv_desc_fill: K=%d not supported (<= 32)", K);
+  OSB_CHECK(nbr != nullptr || K == 1, "osb_conv_desc_fill: identity map needs K == 1");
+  OSB_CHECK(n_out > 0 && n_out < (1ll << 31), "osb_conv_desc_fill: bad row count");
+  OSB_CHECK(cout % 32 == 0 && cout > 0, "osb_conv_desc_fill: cout (%d) must be a multiple of 32", cout);
+  OSB_CHECK(out_split || out_f32, "osb_conv_desc_fill: no output given");
+  OSB_CHECK((scale == nullptr) == (shift == nullptr), "osb_conv_desc_fill: scale and shift go together");
+  OSB_CHECK(cmap == nullptr || (cmap_cout > 0 && cmap_cout % 32 == 0 && cout % cmap_cout == 0 && res == nullptr),
+            "osb_conv_desc_fill: bad dense-transpose arguments");
+  OSB_CHECK((cmap ? cmap_cout : cout) <= CH_SS_FLOATS, "osb_conv_desc_fill: more than %d output channels per row", CH_SS_FLOATS);
+  ConvDesc d{};
+  const int cin = c0 + c1;
+  d.src0 = (const uint8_t *)src0; d.src1 = (const uint8_t *)src1; d.nbr = nbr; d.wtiles = (const uint8_t *)wtiles;
+  d.scale = scale; d.shift = shift; d.res = (const uint8_t *)res; d.out_split = (uint8_t *)out_split; d.out_f32 = out_f32;
+  d.out_row_map = out_row_map; d.cmap = cmap; d.n_out = n_out; d.K = K; d.nb0 = c0 / 32; d.nb1 = c1 / 32;
+  d.cout = cout; d.cout_pad = chain_cout_pad(cout); d.nt = chain_nt(cout); d.n_ntiles = d.cout_pad / d.nt;
+  d.relu = relu; d.cmap_cout = cmap_cout; d.m_tiles = (int)ceil_div(n_out, CH_M);
+  d.nsub_max = (d.nt <= 128 && g_chain_nsub >= 2) ? 2 : 1;
+  d.barrier_before = barrier_before ? 1 : 0;
+  d.nsplit = cmap ? 1 : chain_nsplit(n_out, K, cin, cout, osb_conv_chain_grid(), g_chain_force_split);
+  const int T = K * (cin / 32);
+  d.stages_per_split = (T + d.nsplit - 1) / d.nsplit;
+  d.nsplit = (T + d.stages_per_split - 1) / d.stages_per_split;            // no empty splits
+  d.partial = nullptr;
+  if (d.nsplit > 1) {
+    const size_t need = (size_t)d.nsplit * n_out * d.cout_pad * sizeof(float);
+    OSB_CHECK(ws != nullptr && ws_bytes >= need, "osb_conv_desc_fill: workspace of %zu bytes required (got %zu)", need, ws_bytes);
+    d.partial = (float *)ws;
+  }
+  memcpy(desc_host, &d, sizeof(d));
+  return 0;
+}
+
+int osb_conv_chain_launch(const void *descs_dev, const void *descs_host, int32_t n_layers, void *grid_barrier_dev, int32_t flags,
+                          void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  OSB_CHECK(descs_dev && descs_host && n_layers >= 1, "osb_conv_chain_launch: bad arguments");
+  const ConvDesc *h = (const ConvDesc *)descs_host;
+  int nt_max = 0, need_bar = 0;
+  for (int i = 0; i < n_layers; ++i) {
+    nt_max = std::max(nt_max, h[i].nt);
+    need_bar |= (h[i].barrier_before || h[i].nsplit > 1);
+    OSB_CHECK(i > 0 || !h[i].barrier_before, "osb_conv_chain_launch: the first layer of a launch cannot ask for a barrier");
+    // a split layer's reduce phase is not followed by a barrier: the next layer may only reuse the partial buffer behind one
+    OSB_CHECK(i == 0 || h[i].barrier_before || h[i].nsplit == 1 || h[i - 1].nsplit == 1 || h[i].partial != h[i - 1].partial,
+              "osb_conv_chain_launch: layers %d and %d share a split workspace without a barrier between them", i - 1, i);
+  }
+  OSB_CHECK(!need_bar || grid_barrier_dev != nullptr, "osb_conv_chain_launch: this chain needs the grid-barrier words");
+  const int bslot = nt_max * 128;
+  const int fixed = 1024 + CH_STG_BYTES + 2 * CH_SS_FLOATS * 4 + 256 + 40 * 8 + 64;
+  int sb = g_chain_sb > 0 ? g_chain_sb : (bslot >= 32768 ? 2 : 3);
+  sb = std::min(sb, CH_MAX_SB);
+  int sa = (227 * 1024 - fixed - sb * bslot) / CH_A_BYTES;
+  if (g_chain_sa > 0) sa = std::min(sa, g_chain_sa);
+  sa = std::min(sa, CH_MAX_SA);
+  OSB_CHECK(sa >= 2, "osb_conv_chain_launch: shared memory does not hold two row slots");
+  const size_t smem_bytes = (size_t)sa * CH_A_BYTES + (size_t)sb * bslot + fixed;
+  OSB_SMEM_ATTR_ONCE(k_conv_chain, 227 * 1024);
+  const int grid = osb_conv_chain_grid();
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(CH_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
+  cfg.attrs = attr; cfg.numAttrs = (flags & 1) ? 1 : 0;
+  OSB_CUDA(cudaLaunchKernelEx(&cfg, k_conv_chain, (const ConvDesc *)descs_dev, (int)n_layers, (unsigned *)grid_barrier_dev, sa, sb,
+                              bslot, (int)(flags & 1), g_chain_dbg_clock));
+  OSB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

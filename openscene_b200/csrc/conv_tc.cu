@@ -24,6 +24,7 @@
 //   0           one TMA row load per row (cross-check path).
 #include "tc_ptx.cuh"
 #include <algorithm>
+#include <string>
 
 namespace osb {
 
@@ -560,6 +561,23 @@ static int g_tc_min_stages = 3;
 static int g_tc_lazy = 1;                  // cp.async path: per-offset index fetch instead of the smem index prologue            // fewest stages accepted for the multi-CTA-per-SM configuration
 static long long *g_tc_dbg_clock = nullptr;
 
+// knobs of this kernel behind osb_tuning_set (conv_chain.cu); returns false for names it does not own
+bool conv_tc_tuning(const char *name, int64_t v) {
+  const std::string n(name);
+  if (n == "tc_a_path") g_tc_use_gather4 = (int)v;            // 2 = cp.async (default), 1 = TMA gather4, 0 = TMA row loads
+  else if (n == "tc_smem_budget") g_tc_smem_budget = (int)v;  // per CTA; 112 KB -> two CTAs per SM
+  else if (n == "tc_dbg_skip") g_tc_dbg_skip = (int)v;
+  else if (n == "tc_force_split") g_tc_force_split = (int)v;
+  else if (n == "tc_target_ctas") g_tc_target_ctas = (int)v;
+  else if (n == "tc_pf_dist") g_tc_pf_dist = (int)v;
+  else if (n == "tc_small_nt") g_tc_small_nt = (int)v;
+  else if (n == "tc_min_stages") g_tc_min_stages = (int)v;
+  else if (n == "tc_lazy") g_tc_lazy = (int)v;
+  else if (n == "tc_dbg_clock") g_tc_dbg_clock = (long long *)(intptr_t)v;
+  else return false;
+  return true;
+}
+
 }  // namespace osb
 
 using namespace osb;
@@ -574,22 +592,6 @@ static inline int choose_nt(int64_t n_out, int cp) {
 }
 
 extern "C" {
-
-// test / tuning hooks (not part of the public header): 0/1 gather4, shared-memory budget per CTA
-void osb_debug_set_tc(int use_gather4, int smem_budget) {
-  if (use_gather4 >= 0) g_tc_use_gather4 = use_gather4;
-  if (smem_budget > 0) g_tc_smem_budget = smem_budget;
-}
-void osb_debug_set_tc3(int pf_dist) { g_tc_pf_dist = pf_dist; }
-void osb_debug_set_tc4(int small_nt, int small_rows) { g_tc_small_nt = small_nt; if (small_rows > 0) g_tc_small_rows = small_rows; }
-void osb_debug_set_tc5(int min_stages) { g_tc_min_stages = min_stages; }
-void osb_debug_set_tc6(int lazy) { g_tc_lazy = lazy; }
-void osb_debug_set_clock(void *buf) { g_tc_dbg_clock = (long long *)buf; }
-void osb_debug_set_tc2(int dbg_skip, int force_split, int target_ctas) {
-  if (dbg_skip >= 0) g_tc_dbg_skip = dbg_skip;
-  if (force_split >= 0) g_tc_force_split = force_split;
-  if (target_ctas > 0) g_tc_target_ctas = target_ctas;
-}
 
 // bytes of caller-provided scratch osb_conv_fwd_tc may need for this shape (0 = none)
 size_t osb_conv_tc_workspace_bytes(int64_t n_out, int32_t K, int32_t cin, int32_t cout) {

@@ -36,9 +36,13 @@ def _fold_bn(bn_module):
 
 class _Conv:
     """Packed weights + folded BN of one convolution."""
-    __slots__ = ('K', 'cin', 'cout', 'wpack', 'w3', 'scale', 'shift', 'ks', 'stride', 'transpose', 'wpack_a', 'scale_a', 'shift_a')
+    __slots__ = ('K', 'cin', 'cout', 'wpack', 'w3', 'scale', 'shift', 'ks', 'stride', 'transpose', 'wpack_a', 'scale_a', 'shift_a',
+                 'wtiles', 'wtiles_a', 'n_ntiles')
 
     def __init__(self, conv, bn=None, keep_f32=False):
+        if getattr(conv, 'bias', None) is not None:
+            raise NotImplementedError("FusedMinkUNet: convolutions with bias are not folded (no MinkUNet layer has one: "
+                                      "models/mink_unet.py builds every convolution with bias=False)")
         w3 = conv.kernel.detach()
         w3 = w3.unsqueeze(0) if w3.dim() == 2 else w3
         self.K, self.cin, self.cout = w3.shape
@@ -49,6 +53,9 @@ class _Conv:
         self.scale, self.shift = _fold_bn(bn) if bn is not None else (None, None)
         # raw device addresses for the low-overhead launch path (tensors above keep the memory alive)
         self.wpack_a = self.wpack.data_ptr() if self.wpack is not None else 0
+        self.wtiles = tc.pack_weight_tiles(w3) if self.wpack is not None else None        # persistent-kernel packing
+        self.wtiles_a = self.wtiles.data_ptr() if self.wtiles is not None else 0
+        self.n_ntiles = max(1, -(-self.cout // 256))
         self.scale_a = self.scale.data_ptr() if self.scale is not None else 0
         self.shift_a = self.shift.data_ptr() if self.shift is not None else 0
 
@@ -79,6 +86,9 @@ class FusedMinkUNet:
                     wide = m.kernel.detach().permute(1, 0, 2).reshape(1, up.cin, up.K * up.cout).contiguous()
                     up.wpack = tc.pack_weights(wide)
                     up.wpack_a = up.wpack.data_ptr()
+                    up.wtiles = tc.pack_weight_tiles(wide)
+                    up.wtiles_a = up.wtiles.data_ptr()
+                    up.n_ntiles = max(1, -(-(up.K * up.cout) // 256))
                 self.dec.append((up, self._blocks(getattr(net, f'block{j + 1}'))))
             self.final = _Conv(net.final, None, keep_f32=True)
         self.out_channels = self.final.cout
@@ -86,6 +96,10 @@ class FusedMinkUNet:
         self._ws = None
         self._arena = None
         self.use_pdl = os.environ.get('OSB_PDL', '1') != '0'
+        # persistent chain kernel (csrc/conv_chain.cu); OSB_CHAIN=0 restores one launch of the first-generation kernel per layer
+        self.use_chain = os.environ.get('OSB_CHAIN', '1') != '0'
+        self.chain_max_tiles = int(os.environ.get('OSB_CHAIN_MAX_TILES', '-1'))   # layers up to this many (row x N) tiles share a launch
+        self._chain = None
         self.use_pyramid = os.environ.get('OSB_PYRAMID', '1') != '0'
         if 'OSB_TC_LAZY' in os.environ:                      # tuning: 0 = smem index prologue, 1 = lazy on >= 2-wave launches, 2 = always
             tc.debug_set_tc(lazy=int(os.environ['OSB_TC_LAZY']))
@@ -119,7 +133,28 @@ class FusedMinkUNet:
                 total += _al(n[l] * 4 * c1.cout) + _al(n[l] * 4 * c2.cout) + (_al(n[l] * 4 * ds.cout) if ds else 0)
         return total
 
-    def _conv(self, cv, srcs, nbr_a, n_out, res_a=0, relu=1, out_f32_a=0, row_map_a=0):
+    def _chain_add(self, cv, s0, c0, s1, c1, nbr_a, n_rows, K, cout, res_a, relu, out_a, out_f32_a, row_map_a, cmap_a, cmap_cout,
+                   independent=False):
+        """Record one layer of the persistent chain.  Layers whose (row tile x N tile) count is at most `chain_max_tiles`
+        share a launch with their neighbours (grid barrier between dependent layers); larger layers get their own launch.
+        `independent`: the layer reads nothing the previous layer of the chain wrote (BasicBlock downsample next to conv1)."""
+        ch = self._chain
+        tiles = -(-n_rows // 128) * max(1, -(-cout // 256))
+        small = tiles <= self._chain_small
+        if not (small and self._chain_prev_small):
+            ch.cut()
+        self._chain_prev_small = small
+        ws_bytes = 0 if cmap_a else self._ws_query(n_rows, K, c0 + c1, cout)
+        ws_a = 0
+        if ws_bytes:
+            self._ws_flip ^= 1                                   # consecutive split layers never share scratch
+            ws_a = self._ws_a + self._ws_flip * (self._ws_bytes // 2)
+            if ws_bytes > self._ws_bytes // 2:
+                raise RuntimeError(f"FusedMinkUNet: split workspace of {ws_bytes} bytes exceeds the {self._ws_bytes // 2} provided")
+        ch.add(s0, c0, s1, c1, nbr_a, n_rows, K, cv.wtiles_a, cout, cv.scale_a, cv.shift_a, res_a, relu, out_a, out_f32_a, row_map_a,
+               cmap_a, cmap_cout, ws_a, ws_bytes, 0 if independent else 1)
+
+    def _conv(self, cv, srcs, nbr_a, n_out, res_a=0, relu=1, out_f32_a=0, row_map_a=0, independent=False):
         """srcs: [(addr, channels, rows)] (one or two).  Returns the address of the split output (or 0)."""
         (s0, c0, r0) = srcs[0]
         (s1, c1, r1) = srcs[1] if len(srcs) > 1 else (0, 0, 0)
@@ -127,18 +162,26 @@ class FusedMinkUNet:
         if not out_f32_a:
             out_a = self._cursor
             self._cursor += _al(n_out * 4 * cv.cout)
+        if self._chain_on:
+            self._chain_add(cv, s0, c0, s1, c1, nbr_a, n_out, cv.K, cv.cout, res_a, relu, out_a, out_f32_a, row_map_a, 0, 0,
+                            independent=independent)
+            return out_a
         rc = self._fn(s0, c0, r0, s1, c1, r1, nbr_a, n_out, cv.K, cv.wpack_a, cv.cout, cv.scale_a, cv.shift_a, res_a, relu,
                       out_a, out_f32_a, row_map_a, self._ws_a, self._ws_bytes, self._flags, self._stream)
         if rc:
             C.check(rc, 'osb_conv_fwd_tc')
         return out_a
 
+    def _chain_run(self):
+        if self._chain_on:
+            self._chain.run(self._flags, self._stream)
+
     def _stage(self, blocks, srcs, nbr3_a, n):
         x = srcs
         for (c1, c2, ds) in blocks:
             y = self._conv(c1, x, nbr3_a, n)
             if ds is not None:
-                r = self._conv(ds, x, 0, n, relu=0)
+                r = self._conv(ds, x, 0, n, relu=0, independent=True)
             else:
                 r = x[0][0]
             x = [(self._conv(c2, [(y, c1.cout, n)], nbr3_a, n, res_a=r), c2.cout, n)]
@@ -170,10 +213,20 @@ class FusedMinkUNet:
                 self._arena = torch.empty(int(need * 1.25), dtype=torch.uint8, device=self.device)
             self._cursor = _al(self._arena.data_ptr())
             if self._ws is None:
-                self._ws = torch.empty(96 << 20, dtype=torch.uint8, device=self.device)
+                self._ws = torch.empty(192 << 20, dtype=torch.uint8, device=self.device)      # two halves: consecutive split layers alternate
             self._ws_a, self._ws_bytes = self._ws.data_ptr(), self._ws.numel()
             self._stream = torch.cuda.current_stream().cuda_stream
             self._fn = C.lib().osb_conv_fwd_tc
+            self._chain_on = self.use_chain
+            if self._chain_on:
+                if self._chain is None:
+                    self._chain = tc.ConvChain(self.device, 160)
+                    self._ws_query = C.lib().osb_conv_chain_workspace_bytes
+                self._chain.begin()
+                grid = C.lib().osb_conv_chain_grid()
+                self._chain_small = self.chain_max_tiles if self.chain_max_tiles >= 0 else 2 * grid
+                self._chain_prev_small = False
+                self._ws_flip = 0
             # PDL: every kernel map / packed weight / BN constant is complete before the chain starts (maps are built
             # above, the stem kernel sits between them and the first convolution)
             self._flags = 1 if self.use_pdl else 0
@@ -199,7 +252,12 @@ class FusedMinkUNet:
                 skips.append(cur)
             for j, (uconv, blocks) in enumerate(self.dec):
                 l = 3 - j                                   # output level of this transposed conv
-                if self.dense_up:
+                if self.dense_up and self._chain_on:
+                    y = self._cursor
+                    self._cursor += _al(n[l] * 4 * uconv.cout)
+                    self._chain_add(uconv, cur[0], cur[1], 0, 0, 0, n[l + 1], 1, uconv.K * uconv.cout, 0, 1, y, 0, 0,
+                                    down[l].nbr.data_ptr(), uconv.cout)
+                elif self.dense_up:
                     y = self._cursor
                     self._cursor += _al(n[l] * 4 * uconv.cout)
                     rc = C.lib().osb_convtr_fwd_tc(cur[0], cur[1], n[l + 1], down[l].nbr.data_ptr(), uconv.K, uconv.wpack_a,
@@ -212,12 +270,15 @@ class FusedMinkUNet:
             if head is not None:                           # folded head: 96 -> (96 + K) conv, rows straight in caller order
                 z = torch.empty((n[0], head.cout), dtype=torch.float32, device=self.device)
                 self._conv(head, [cur], 0, n[0], relu=0, out_f32_a=z.data_ptr(), row_map_a=cm.perm.data_ptr())
+                self._chain_run()
                 return z
             fin = self.final
             out = torch.empty((n[0], fin.cout), dtype=torch.float32, device=self.device)
             if fin.wpack is not None:
                 self._conv(fin, [cur], 0, n[0], relu=0, out_f32_a=out.data_ptr(), row_map_a=cm.perm.data_ptr())
+                self._chain_run()
                 return out
+            self._chain_run()
             # odd head width (e.g. 20 classes): generic fp32 kernel, then restore the caller's order
             xf = torch.empty((n[0], cur[1]), dtype=torch.float32, device=self.device)
             C.call('osb_split_to_f32', cur[0], n[0], cur[1], C.ptr(xf), C.stream_ptr())
@@ -247,8 +308,10 @@ class FusedMinkUNet:
         cv = _Conv.__new__(_Conv)
         cv.K, cv.cin, cv.cout, cv.ks, cv.stride, cv.transpose = 1, cin, cout, 1, 1, False
         cv.w3, cv.wpack = w, tc.pack_weights(w)
+        cv.wtiles = tc.pack_weight_tiles(w)
         cv.scale = cv.shift = None
-        cv.wpack_a, cv.scale_a, cv.shift_a = cv.wpack.data_ptr(), 0, 0
+        cv.wpack_a, cv.wtiles_a, cv.scale_a, cv.shift_a = cv.wpack.data_ptr(), cv.wtiles.data_ptr(), 0, 0
+        cv.n_ntiles = max(1, -(-cout // 256))
         return (cv, cin, k)
 
     @torch.no_grad()

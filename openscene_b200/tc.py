@@ -70,33 +70,122 @@ def conv_stem(x, coords, slots, cap, ks, step, w3, scale=None, shift=None, relu=
     return os_, of_
 
 
+def pack_weight_tiles(w3, transpose_w=False):
+    """w3 fp32 [K, cin, cout] (or [K, cout, cin] with transpose_w) -> tile-major pre-swizzled B operands of the
+    persistent kernel (csrc/conv_chain.cu)."""
+    w3 = w3.detach().contiguous().float()
+    K = w3.shape[0]
+    cin, cout = (w3.shape[2], w3.shape[1]) if transpose_w else (w3.shape[1], w3.shape[2])
+    nbytes = C.lib().osb_conv_weight_tiles_bytes(K, cin, cout)
+    out = torch.empty(nbytes, dtype=torch.uint8, device=w3.device)
+    C.call('osb_conv_pack_weight_tiles', C.ptr(w3), K, cin, cout, int(transpose_w), C.ptr(out), C.stream_ptr())
+    return out
+
+
+class ConvChain:
+    """A list of convolution layers executed by osb_conv_chain_launch (one persistent launch per group of layers).
+
+    Descriptors are filled into pinned host memory with raw device addresses (ints), copied to the device once per
+    forward, and launched group by group: ``begin()``, ``add(...)`` per layer, ``cut()`` between launches, ``run()``."""
+
+    def __init__(self, device, max_layers=160):
+        self.device = torch.device(device)
+        self.dbytes = C.lib().osb_conv_desc_bytes()
+        self.max_layers = max_layers
+        # pageable on purpose: the H2D copy below is then staged by the driver before copy_ returns, so the next forward may
+        # refill this buffer while the GPU is still several steps behind
+        self.host = torch.zeros(max_layers * self.dbytes, dtype=torch.uint8)
+        with torch.cuda.device(self.device):
+            self.dev = torch.empty(max_layers * self.dbytes, dtype=torch.uint8, device=self.device)
+            self.gbar = torch.zeros(4, dtype=torch.int32, device=self.device)       # {count, generation}: zeroed once
+        self.host_a, self.dev_a, self.gbar_a = self.host.data_ptr(), self.dev.data_ptr(), self.gbar.data_ptr()
+        self._fill = C.lib().osb_conv_desc_fill
+        self.begin()
+
+    def begin(self):
+        self.n = 0
+        self.groups = []
+        self._g0 = 0
+
+    def add(self, src0, c0, src1, c1, nbr, n_out, K, wtiles, cout, scale=0, shift=0, res=0, relu=0, out_split=0, out_f32=0,
+            row_map=0, cmap=0, cmap_cout=0, ws=0, ws_bytes=0, barrier_before=0):
+        """All pointer arguments are raw device addresses (0 = NULL)."""
+        if self.n >= self.max_layers:
+            raise RuntimeError("ConvChain: too many layers")
+        rc = self._fill(self.host_a + self.n * self.dbytes, src0, c0, src1 or None, c1, nbr or None, n_out, K, wtiles, cout,
+                        scale or None, shift or None, res or None, int(relu), out_split or None, out_f32 or None,
+                        row_map or None, cmap or None, cmap_cout, ws or None, ws_bytes,
+                        int(bool(barrier_before) and self.n > self._g0))
+        if rc:
+            C.check(rc, 'osb_conv_desc_fill')
+        self.n += 1
+
+    def cut(self):
+        """End the current launch group (the next layer starts a new launch)."""
+        if self.n > self._g0:
+            self.groups.append((self._g0, self.n - self._g0))
+            self._g0 = self.n
+
+    def run(self, flags=0, stream=None):
+        self.cut()
+        stream = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        with torch.cuda.device(self.device):
+            self.dev[:self.n * self.dbytes].copy_(self.host[:self.n * self.dbytes], non_blocking=True)
+        fn = C.lib().osb_conv_chain_launch
+        for (g0, cnt) in self.groups:
+            rc = fn(self.dev_a + g0 * self.dbytes, self.host_a + g0 * self.dbytes, cnt, self.gbar_a, flags, stream)
+            if rc:
+                C.check(rc, 'osb_conv_chain_launch')
+
+
+_CHAINS = {}
+
+
+def conv_chain_single(src0, c0, src1, c1, nbr, n_out, K, wtiles, cout, scale=None, shift=None, res=None, relu=False,
+                      out_split=True, out_f32=False, out_row_map=None, cmap=None, cmap_cout=0, n_rows_out=None):
+    """One convolution through the persistent kernel (tests / module surface).  Same meaning as ``conv_tc``;
+    ``cmap`` selects the dense transposed form (outputs then have ``n_rows_out`` rows of ``cmap_cout`` channels)."""
+    dev = src0.device
+    rows = n_rows_out if n_rows_out is not None else n_out
+    oc = cmap_cout if cmap is not None else cout
+    a = lambda t: 0 if t is None else t.data_ptr()
+    with torch.cuda.device(dev):
+        os_ = torch.empty((rows, 4 * oc), dtype=torch.uint8, device=dev) if out_split else None
+        of_ = torch.empty((rows, oc), dtype=torch.float32, device=dev) if out_f32 else None
+        ws_bytes = 0 if cmap is not None else C.lib().osb_conv_chain_workspace_bytes(n_out, K, c0 + c1, cout)
+        ws = _workspace(dev, ws_bytes) if ws_bytes else None
+        ch = _CHAINS.get(dev)
+        if ch is None:
+            ch = _CHAINS[dev] = ConvChain(dev, 8)
+        ch.begin()
+        ch.add(a(src0), c0, a(src1), c1, a(nbr), n_out, K, a(wtiles), cout, a(scale), a(shift), a(res), int(relu), a(os_), a(of_),
+               a(out_row_map), a(cmap), cmap_cout, a(ws), ws_bytes, 0)
+        ch.run()
+    return os_, of_
+
+
+def tuning_set(name, value):
+    """Process-wide tuning knob of libosb200 (osb_tuning_set; never changes results)."""
+    C.call('osb_tuning_set', name.encode(), int(value))
+
+
 def debug_set_tc(use_gather4=-1, smem_budget=0, dbg_skip=-1, force_split=-1, target_ctas=0, pf_dist=None, small_nt=None, min_stages=None, lazy=None):
-    fn = C.lib().osb_debug_set_tc
-    fn.restype, fn.argtypes = None, [ctypes.c_int, ctypes.c_int]
-    fn(use_gather4, smem_budget)
-    fn2 = C.lib().osb_debug_set_tc2
-    fn2.restype, fn2.argtypes = None, [ctypes.c_int, ctypes.c_int, ctypes.c_int]
-    fn2(dbg_skip, force_split, target_ctas)
-    if pf_dist is not None:
-        fn3 = C.lib().osb_debug_set_tc3
-        fn3.restype, fn3.argtypes = None, [ctypes.c_int]
-        fn3(pf_dist)
-    if small_nt is not None:
-        fn4 = C.lib().osb_debug_set_tc4
-        fn4.restype, fn4.argtypes = None, [ctypes.c_int, ctypes.c_int]
-        fn4(small_nt, 0)
-    if min_stages is not None:
-        fn5 = C.lib().osb_debug_set_tc5
-        fn5.restype, fn5.argtypes = None, [ctypes.c_int]
-        fn5(min_stages)
-    if lazy is not None:
-        fn6 = C.lib().osb_debug_set_tc6
-        fn6.restype, fn6.argtypes = None, [ctypes.c_int]
-        fn6(lazy)
+    """Knobs of the first-generation kernel (csrc/conv_tc.cu)."""
+    if use_gather4 >= 0:
+        tuning_set('tc_a_path', use_gather4)
+    if smem_budget > 0:
+        tuning_set('tc_smem_budget', smem_budget)
+    if dbg_skip >= 0:
+        tuning_set('tc_dbg_skip', dbg_skip)
+    if force_split >= 0:
+        tuning_set('tc_force_split', force_split)
+    if target_ctas > 0:
+        tuning_set('tc_target_ctas', target_ctas)
+    for name, v in (('tc_pf_dist', pf_dist), ('tc_small_nt', small_nt), ('tc_min_stages', min_stages), ('tc_lazy', lazy)):
+        if v is not None:
+            tuning_set(name, v)
 
 
 def debug_set_clock(buf):
     """tuning: int64 CUDA tensor [n_tiles, 8] receiving per-CTA clock64 stamps (None disables)."""
-    fn = C.lib().osb_debug_set_clock
-    fn.restype, fn.argtypes = None, [ctypes.c_void_p]
-    fn(C.ptr(buf))
+    tuning_set('tc_dbg_clock', buf.data_ptr() if buf is not None else 0)
