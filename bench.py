@@ -35,7 +35,8 @@ def parse():
     ap.add_argument('--impl', default='osb200', choices=['osb200', 'reference'])
     ap.add_argument('--workload', default='config2_200k')
     ap.add_argument('--arch', default='MinkUNet34C')
-    ap.add_argument('--k-text', type=int, default=20)
+    ap.add_argument('--k-text', type=int, default=None, help='text embeddings (default 20; 160 for config4_matterport, 16 for config5_lidar)')
+    ap.add_argument('--match', default=None, choices=['cosine', 'ensemble'], help="matching step: cosine (default) or run/evaluate.py's ensemble path (default for config4_matterport)")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--modules', action='store_true', help='time the module-by-module MinkowskiEngine surface instead of the fused engine')
     return ap.parse_args()
@@ -159,7 +160,8 @@ def host_threads():
 def workload_config(args, n_vox):
     """The `config` object, identical in both arms (the driver compares them)."""
     return {'workload': f'{args.workload}: {n_vox} voxels/scene, one scene per GPU, {args.arch}, 768-d head, '
-                        f'K_text={args.k_text}, cosine (L2-normalised) scores + argmax',
+                        f'K_text={args.k_text}, ' + ('ensemble matching (2 cosine products + select + final product, run/evaluate.py:302-323)'
+                                                      if getattr(args, 'match', 'cosine') == 'ensemble' else 'cosine (L2-normalised) scores') + ' + argmax',
             'points': 'stride-1 voxels fed to SparseTensor',
             'l2': 'GPU arm: L2 flushed (256 MiB memset) before every timed step; CPU arm: working set (~2 GB of activations) '
                   'far beyond the last-level cache'}
@@ -204,6 +206,10 @@ def run_reference(args, rank):
 
 def main():
     args = parse()
+    if args.k_text is None:
+        args.k_text = {'config4_matterport': 160, 'config5_lidar': 16}.get(args.workload, 20)
+    if args.match is None:
+        args.match = 'ensemble' if args.workload == 'config4_matterport' else 'cosine'
     rank = int(os.environ.get('RANK', 0))
     local = int(os.environ.get('LOCAL_RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
@@ -230,13 +236,24 @@ def main():
     eng = engine.FusedMinkUNet(model)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
+    feat2d = None
+    if args.match == 'ensemble':                                    # fused 2-D features of the scene, fp16 as stored (fusion_util.py:87)
+        g2 = torch.Generator(device=dev).manual_seed(11 + rank)
+        feat2d = (torch.randn(n0, 768, device=dev, generator=g2) * 0.3).half()
+
+    def match(out):
+        if args.match == 'ensemble':                                 # run/evaluate.py:302-323: two cosine products, select, final product
+            s_, l_, _, _ = matching.match_ensemble(out, feat2d, None, text)
+            return s_, l_, None
+        return matching._scores(out, None, text, normalize=True)
+
     def step_device():
         if args.modules:
             with torch.no_grad():                                    # as run/evaluate.py:260
                 out = model(ME.SparseTensor(feats_dev, coords_dev))
         else:
             out = eng(coords_dev, feats_dev)
-        return matching._scores(out, None, text, normalize=True)
+        return match(out)
 
     label_host = [torch.empty(n0, dtype=torch.int64).pin_memory() for _ in range(4)]   # ring of pinned result buffers
     e2e_i = [0]
@@ -249,7 +266,7 @@ def main():
         f = feats_host.to(dev, non_blocking=True)
         with torch.no_grad():
             out = model(ME.SparseTensor(f, c)) if args.modules else eng(c, f)
-        _, label, _ = matching._scores(out, None, text, normalize=True)
+        _, label, _ = match(out)
         buf = label_host[e2e_i[0] % len(label_host)]
         e2e_i[0] += 1
         buf.copy_(label, non_blocking=True)

@@ -8,7 +8,7 @@
 // their loops between units:
 //
 //   warp 0      weight tiles: one cp.async.bulk per stage from the tile-major, pre-swizzled packing (no tensor map)
-//   warp 1      TMEM owner + single-thread tcgen05.mma issuer
+//   warps 1-2   tcgen05.mma issuers (one thread each): warp 1 owns sub-tile 0 of an item, warp 2 sub-tile 1; warp 1 owns TMEM
 //   warps 4-7   gathered A rows: cp.async 16 B x 8 lanes per 128-byte row line, hand-applied 128B swizzle, the kernel
 //               map read per offset straight from global memory, one offset ahead
 //   warps 8-15  two epilogue groups, one per TMEM accumulator buffer: TMEM -> registers -> BN affine / residual / ReLU ->
@@ -121,9 +121,9 @@ k_conv_chain(const ConvDesc *__restrict__ descs, int n_layers, unsigned *gbar, i
   const uint32_t accFull = smem_u32(bars + 32), accEmpty = smem_u32(bars + 34);
 
   if (tid == 0) {
-    for (int s = 0; s < sa; ++s) { mbar_init(fullA + 8 * s, 128); mbar_init(emptyA + 8 * s, 1); }
-    for (int s = 0; s < sb; ++s) { mbar_init(fullB + 8 * s, 1); mbar_init(emptyB + 8 * s, 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(accFull + 8 * b, 1); mbar_init(accEmpty + 8 * b, 4); }
+    for (int s = 0; s < sa; ++s) { mbar_init(fullA + 8 * s, (flags & 0x8000) ? 4 : 128); mbar_init(emptyA + 8 * s, 1); }
+    for (int s = 0; s < sb; ++s) { mbar_init(fullB + 8 * s, 1); mbar_init(emptyB + 8 * s, 2); }   // emptyB: one arrival per issuer
+    for (int b = 0; b < 2; ++b) { mbar_init(accFull + 8 * b, 2); mbar_init(accEmpty + 8 * b, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {   // all 512 TMEM columns: two accumulator buffers of 256 columns (one CTA per SM, no contention)
@@ -184,48 +184,67 @@ k_conv_chain(const ConvDesc *__restrict__ descs, int n_layers, unsigned *gbar, i
           mbar_wait(emptyB + 8 * b_slot, b_phase ^ 1);
           if (elect_one()) {
             const uint32_t fb = fullB + 8 * b_slot;
-            mbar_expect_tx(fb, b_bytes);
-            bulk_g2s(smem_u32(smem_b + b_slot * bslot), d.wtiles + ((int64_t)t * d.n_ntiles + nti) * b_bytes, b_bytes, fb);
+            if (flags & 0x200) {                      // tuning: no weight loads
+              mbar_expect_tx(fb, 0u);
+            } else {
+              mbar_expect_tx(fb, b_bytes);
+              bulk_g2s(smem_u32(smem_b + b_slot * bslot), d.wtiles + ((int64_t)t * d.n_ntiles + nti) * b_bytes, b_bytes, fb);
+            }
           }
           __syncwarp();
           if (++b_slot == (uint32_t)sb) { b_slot = 0; b_phase ^= 1; }
         }
       }
-    } else if (warp == 1) {
-      // ================================ MMA issuer ===================================
+    } else if (warp == 1 || warp == 2) {
+      // ============ MMA issuers: warp 1 owns sub-tile 0 of every item, warp 2 sub-tile 1 ===============
+      // One issuing thread pays ~300-500 cycles of barrier-wait / proxy-fence / commit latency per row slot, more than
+      // the 288 cycles of tensor work a 96-channel slot carries; two issuers on disjoint accumulator columns restore the
+      // slack two co-resident CTAs used to give.  Each sub-tile's MMAs are issued by one thread, in stage order.
+      const int mi = warp - 1;
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(d.nt >> 3) << 17) | ((uint32_t)(CH_M >> 4) << 24);
       CH_FOR_ITEMS() {
         (void)m; (void)nti;
         const uint32_t buf = n_item & 1u;
-        mbar_wait(accEmpty + 8 * buf, ((n_item >> 1) & 1u) ^ 1u);         // the epilogue drained this buffer
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const bool mine = mi < nsub;
+        if (mine) {
+          mbar_wait(accEmpty + 8 * buf, ((n_item >> 1) & 1u) ^ 1u);       // the epilogue drained this buffer
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        const uint32_t dcol = tmem_base + buf * 256u + (uint32_t)mi * 128u;
         for (int t = t_begin; t < t_end; ++t) {
-          mbar_wait(fullB + 8 * b_slot, b_phase);
-          const uint64_t db = umma_desc(smem_u32(smem_b + b_slot * bslot));
-          for (int s = 0; s < nsub; ++s) {
-            mbar_wait(fullA + 8 * a_slot, a_phase);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) writes -> UMMA reads
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (elect_one()) {
-              const uint64_t da = umma_desc(smem_u32(smem + a_slot * CH_A_BYTES));
-              const uint32_t dcol = tmem_base + buf * 256u + (uint32_t)s * 128u;
+          if (mine) {
+            uint32_t sl = a_slot + (uint32_t)mi, ph = a_phase;             // my row slot of this stage
+            if (sl >= (uint32_t)sa) { sl -= (uint32_t)sa; ph ^= 1u; }
+            mbar_wait(fullB + 8 * b_slot, b_phase);
+            mbar_wait(fullA + 8 * sl, ph);
+            if (!(flags & 0x1000)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) writes -> UMMA reads
+            if (!(flags & 0x2000)) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (flags & 0x4000) {                     // tuning: plain arrivals instead of tcgen05.commit (only without MMAs)
+              if (lane == 0) { mbar_arrive(emptyA + 8 * sl); mbar_arrive(emptyB + 8 * b_slot); }
+            } else if (elect_one()) {
+              const uint64_t db = umma_desc(smem_u32(smem_b + b_slot * bslot));
+              const uint64_t da = umma_desc(smem_u32(smem + sl * CH_A_BYTES));
               // 128-byte line = [hi ch0-15 | hi ch16-31 | lo ch0-15 | lo ch16-31]; +2 per 32-byte K slice
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
+                if (flags & 0x400) break;             // tuning: no MMAs
                 umma_bf16(dcol, da + 2 * h, db + 2 * h, idesc, (h == 0 && t == t_begin) ? 0u : 1u);   // hi * Whi
                 umma_bf16(dcol, da + 2 * h, db + 2 * h + 4, idesc, 1u);                                // hi * Wlo
                 umma_bf16(dcol, da + 2 * h + 4, db + 2 * h, idesc, 1u);                                // lo * Whi
               }
-              umma_commit(emptyA + 8 * a_slot);                             // row slot free when these MMAs retire
+              umma_commit(emptyA + 8 * sl);                                 // row slot free when these MMAs retire
+              umma_commit(emptyB + 8 * b_slot);                             // weight slot: one arrival per issuer
             }
-            __syncwarp();
-            if (++a_slot == (uint32_t)sa) { a_slot = 0; a_phase ^= 1; }
+          } else if (lane == 0) {
+            mbar_arrive(emptyB + 8 * b_slot);                               // nothing of mine reads this weight tile
           }
-          if (elect_one()) umma_commit(emptyB + 8 * b_slot);
           __syncwarp();
+          a_slot += (uint32_t)nsub;
+          if (a_slot >= (uint32_t)sa) { a_slot -= (uint32_t)sa; a_phase ^= 1u; }
           if (++b_slot == (uint32_t)sb) { b_slot = 0; b_phase ^= 1; }
         }
-        if (elect_one()) umma_commit(accFull + 8 * buf);
+        if (mine) { if (elect_one()) umma_commit(accFull + 8 * buf); }
+        else if (lane == 0) mbar_arrive(accFull + 8 * buf);
         __syncwarp();
         ++n_item;
       }
@@ -266,15 +285,18 @@ k_conv_chain(const ConvDesc *__restrict__ descs, int n_layers, unsigned *gbar, i
             for (int s = 0; s < nsub; ++s) {
               mbar_wait(emptyA + 8 * a_slot, a_phase ^ 1);
               const uint32_t a_dst = smem_u32(smem + a_slot * CH_A_BYTES) + (w * 32 + q) * 128;
+              if (!(flags & 0x100)) {                 // tuning: bit 8 = no row copies
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int m7 = (4 * i + q) & 7;
-                const int32_t r = (s == 0) ? cur[0][i] : cur[1][i];
-                const bool valid = r >= 0;
-                const uint8_t *sp = valid ? src + (int64_t)r * row_bytes + col_byte : src;
-                cp_async16(a_dst + i * 512 + ((j ^ m7) << 4), sp, valid ? 16u : 0u);      // size 0 -> zero fill
+                for (int i = 0; i < 8; ++i) {
+                  const int m7 = (4 * i + q) & 7;
+                  const int32_t r = (s == 0) ? cur[0][i] : cur[1][i];
+                  const bool valid = r >= 0;
+                  const uint8_t *sp = valid ? src + (int64_t)r * row_bytes + col_byte : src;
+                  cp_async16(a_dst + i * 512 + ((j ^ m7) << 4), sp, valid ? 16u : 0u);      // size 0 -> zero fill
+                }
               }
-              cp_async_arrive_noinc(fullA + 8 * a_slot);
+              if (flags & 0x8000) { __syncwarp(); if (lane == 0) mbar_arrive(fullA + 8 * a_slot); }   // tuning: one arrival per warp
+              else cp_async_arrive_noinc(fullA + 8 * a_slot);
               if (++a_slot == (uint32_t)sa) { a_slot = 0; a_phase ^= 1; }
             }
           }
@@ -312,7 +334,7 @@ k_conv_chain(const ConvDesc *__restrict__ descs, int n_layers, unsigned *gbar, i
               const int r = 4 * i + rsub;
               const int32_t mo = __shfl_sync(0xffffffffu, my_orow, r);
               const int64_t grow = mapped ? (int64_t)mo : wrow0 + r;
-              if (wrow0 + r < d.n_out && grow >= 0)
+              if (wrow0 + r < d.n_out && grow >= 0 && !(flags & 0x800))
                 *reinterpret_cast<uint4 *>(base + grow * row_bytes + col_byte + chunk * 16) = v[i];
             }
           };
@@ -525,6 +547,7 @@ static int g_chain_nsub = 2;             // tuning: 1 = never pair sub-tiles
 static int g_chain_grid = 0;             // tuning: CTAs per launch (0 = one per SM)
 static int g_chain_sa = 0, g_chain_sb = 0;   // tuning: ring depths (0 = as many row slots as fit / 3 or 2 weight slots)
 static long long *g_chain_dbg_clock = nullptr;
+static int g_chain_dbg_skip = 0;         // tuning: bit0 no row copies, bit1 no weight loads, bit2 no MMAs, bit3 no stores
 
 int osb_tuning_set(const char *name, int64_t value) {
   const std::string n(name ? name : "");
@@ -534,6 +557,7 @@ int osb_tuning_set(const char *name, int64_t value) {
   else if (n == "chain_sa") g_chain_sa = (int)value;
   else if (n == "chain_sb") g_chain_sb = (int)value;
   else if (n == "chain_dbg_clock") g_chain_dbg_clock = (long long *)(intptr_t)value;
+  else if (n == "chain_dbg_skip") g_chain_dbg_skip = (int)value;
   else { OSB_CHECK(conv_tc_tuning(n.c_str(), value), "osb_tuning_set: unknown knob '%s'", n.c_str()); }
   return 0;
 }
@@ -622,7 +646,7 @@ int osb_conv_chain_launch(const void *descs_dev, const void *descs_host, int32_t
   cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(CH_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
   cfg.attrs = attr; cfg.numAttrs = (flags & 1) ? 1 : 0;
   OSB_CUDA(cudaLaunchKernelEx(&cfg, k_conv_chain, (const ConvDesc *)descs_dev, (int)n_layers, (unsigned *)grid_barrier_dev, sa, sb,
-                              bslot, (int)(flags & 1), g_chain_dbg_clock));
+                              bslot, (int)((flags & 1) | (g_chain_dbg_skip << 8)), g_chain_dbg_clock));
   OSB_LAUNCH_CHECK();
   return 0;
 }

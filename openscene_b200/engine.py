@@ -100,6 +100,7 @@ class FusedMinkUNet:
         self.use_chain = os.environ.get('OSB_CHAIN', '1') != '0'
         self.chain_max_tiles = int(os.environ.get('OSB_CHAIN_MAX_TILES', '-1'))   # layers up to this many (row x N) tiles share a launch
         self._chain = None
+        self.layer_log = None                     # profiling: set to [] to record (rows, K, cin, cout, tag) per convolution
         self.use_pyramid = os.environ.get('OSB_PYRAMID', '1') != '0'
         if 'OSB_TC_LAZY' in os.environ:                      # tuning: 0 = smem index prologue, 1 = lazy on >= 2-wave launches, 2 = always
             tc.debug_set_tc(lazy=int(os.environ['OSB_TC_LAZY']))
@@ -139,6 +140,8 @@ class FusedMinkUNet:
         share a launch with their neighbours (grid barrier between dependent layers); larger layers get their own launch.
         `independent`: the layer reads nothing the previous layer of the chain wrote (BasicBlock downsample next to conv1)."""
         ch = self._chain
+        if self.layer_log is not None:
+            self.layer_log.append((n_rows, K, c0 + c1, cout, 'dense-up' if cmap_a else ('res' if res_a else '')))
         tiles = -(-n_rows // 128) * max(1, -(-cout // 256))
         small = tiles <= self._chain_small
         if not (small and self._chain_prev_small):
@@ -166,6 +169,8 @@ class FusedMinkUNet:
             self._chain_add(cv, s0, c0, s1, c1, nbr_a, n_out, cv.K, cv.cout, res_a, relu, out_a, out_f32_a, row_map_a, 0, 0,
                             independent=independent)
             return out_a
+        if self.layer_log is not None:
+            self.layer_log.append((n_out, cv.K, c0 + c1, cv.cout, 'res' if res_a else ''))
         rc = self._fn(s0, c0, r0, s1, c1, r1, nbr_a, n_out, cv.K, cv.wpack_a, cv.cout, cv.scale_a, cv.shift_a, res_a, relu,
                       out_a, out_f32_a, row_map_a, self._ws_a, self._ws_bytes, self._flags, self._stream)
         if rc:
@@ -260,6 +265,8 @@ class FusedMinkUNet:
                 elif self.dense_up:
                     y = self._cursor
                     self._cursor += _al(n[l] * 4 * uconv.cout)
+                    if self.layer_log is not None:
+                        self.layer_log.append((n[l + 1], 1, cur[1], uconv.K * uconv.cout, 'dense-up'))
                     rc = C.lib().osb_convtr_fwd_tc(cur[0], cur[1], n[l + 1], down[l].nbr.data_ptr(), uconv.K, uconv.wpack_a,
                                                    uconv.cout, uconv.scale_a, uconv.shift_a, 1, y, 0, self._flags, self._stream)
                     if rc:

@@ -50,32 +50,71 @@ class SparseTensor:
         if device is not None:
             features = features.to(device)
         C.require_cuda(features, 'SparseTensor features')
+        self._cm = self._raw_coords = self._Fi = None
         if coordinate_manager is None:
             if coordinates is None:
                 raise ValueError("SparseTensor needs coordinates or a coordinate_manager")
             ts = tensor_stride if isinstance(tensor_stride, int) else int(tensor_stride[0])
             if ts != 1:
                 raise NotImplementedError("SparseTensor from raw coordinates supports tensor_stride=1 only")
-            coordinate_manager = CoordinateManager(coordinates.to(features.device))
-            coordinate_map_key = CoordinateMapKey(1)
-        elif coordinate_map_key is None:
+            if coordinates.dim() != 2 or coordinates.shape[1] != 4:
+                raise ValueError("coordinates must be [N,4] (batch, x, y, z)")
+            if features.shape[0] != coordinates.shape[0]:
+                raise ValueError(f"features have {features.shape[0]} rows, coordinates have {coordinates.shape[0]}")
+            # The coordinate manager (sort, lookup structures) and the internal-order copy of the features are built on
+            # first use: the fused eval path (fast_eval.py) builds the whole encoder pyramid in one native call instead.
+            self._raw_coords = coordinates.to(features.device)
+            self.coordinate_map_key = CoordinateMapKey(1)
+            self._F_ext = features
+            self._split = None
+            if not torch.is_grad_enabled():
+                from . import fast_eval
+                fast_eval.watch(self)
+            return
+        if coordinate_map_key is None:
             ts = tensor_stride if isinstance(tensor_stride, int) else int(tensor_stride[0])
             coordinate_map_key = CoordinateMapKey(ts)
-        self.coordinate_manager = coordinate_manager
+        self._cm = coordinate_manager
         self.coordinate_map_key = coordinate_map_key
         n = coordinate_manager.sets[coordinate_map_key.ts].n
         if features.shape[0] != n:
             raise ValueError(f"features have {features.shape[0]} rows, coordinate set has {n}")
-        self._F = _to_internal(features, coordinate_manager, coordinate_map_key.ts)
+        self._Fi = _to_internal(features, coordinate_manager, coordinate_map_key.ts)
         self._F_ext = features if coordinate_map_key.ts == 1 else None
         self._split = None
+
+    # -- lazily built state ------------------------------------------------------------------
+    @property
+    def coordinate_manager(self):
+        if self._cm is None:
+            self._cm = CoordinateManager(self._raw_coords)
+        return self._cm
+
+    @coordinate_manager.setter
+    def coordinate_manager(self, cm):
+        self._cm = cm
+
+    @property
+    def _F(self):
+        """features in internal (Morton) row order"""
+        if self._Fi is None:
+            self._Fi = _to_internal(self._F_ext, self.coordinate_manager, self.coordinate_map_key.ts)
+        return self._Fi
+
+    @_F.setter
+    def _F(self, v):
+        self._Fi = v
+
+    def _is_fresh_input(self):
+        """an input tensor straight from ``SparseTensor(features, coordinates)`` that nothing has consumed or modified"""
+        return self._raw_coords is not None and self._Fi is None and self._F_ext is not None
 
     # -- internal constructors ---------------------------------------------------------------
     @classmethod
     def _wrap(cls, F_int, cm, ts):
         t = cls.__new__(cls)
-        t.coordinate_manager, t.coordinate_map_key = cm, CoordinateMapKey(ts)
-        t._F, t._F_ext, t._split = F_int, None, None
+        t._cm, t._raw_coords, t.coordinate_map_key = cm, None, CoordinateMapKey(ts)
+        t._Fi, t._F_ext, t._split = F_int, None, None
         return t
 
     # -- public surface ------------------------------------------------------------------------
@@ -111,23 +150,26 @@ class SparseTensor:
     def D(self):
         return 3
 
+    def _any_F(self):
+        return self._Fi if self._Fi is not None else self._F_ext
+
     @property
     def device(self):
-        return self._F.device
+        return self._any_F().device
 
     @property
     def dtype(self):
-        return self._F.dtype
+        return self._any_F().dtype
 
     @property
     def shape(self):
-        return self._F.shape
+        return self._any_F().shape
 
     def size(self, *a):
-        return self._F.size(*a)
+        return self._any_F().size(*a)
 
     def __len__(self):
-        return self._F.shape[0]
+        return self._any_F().shape[0]
 
     def _same_set(self, o):
         if o.coordinate_manager is not self.coordinate_manager or o._ts != self._ts:
@@ -153,7 +195,7 @@ class SparseTensor:
         return SparseTensor._wrap(self._F * o._F, self.coordinate_manager, self._ts)
 
     def __repr__(self):
-        return f"SparseTensor(N={self._F.shape[0]}, C={self._F.shape[1]}, tensor_stride={self.tensor_stride})"
+        return f"SparseTensor(N={self.shape[0]}, C={self.shape[1]}, tensor_stride={self.tensor_stride})"
 
 
 class _RowGather(torch.autograd.Function):
@@ -269,6 +311,7 @@ def _module_tc_enabled():
 
 
 class _ConvBase(nn.Module):
+    _osb_me_op = True      # an operator of this package (fast_eval.py looks for the module that CALLS them)
     TRANSPOSE = False
 
     def __init__(self, in_channels, out_channels, kernel_size=-1, stride=1, dilation=1, bias=False,
@@ -368,6 +411,7 @@ class MinkowskiConvolutionTranspose(_ConvBase):
 
 
 class MinkowskiBatchNorm(nn.Module):
+    _osb_me_op = True      # an operator of this package (fast_eval.py looks for the module that CALLS them)
     """Same structure as the reference stack: an ``nn.BatchNorm1d`` under ``.bn`` applied to the
     [N,C] feature matrix (resnet_base.py:79-80 touches ``m.bn.weight``).  The fused inference
     engine folds it into the convolution epilogue instead (openscene_b200/engine.py)."""
@@ -385,6 +429,7 @@ class MinkowskiBatchNorm(nn.Module):
 
 
 class MinkowskiReLU(nn.Module):
+    _osb_me_op = True      # an operator of this package (fast_eval.py looks for the module that CALLS them)
     def __init__(self, inplace=False):
         super().__init__()
         self.inplace = inplace
@@ -394,6 +439,7 @@ class MinkowskiReLU(nn.Module):
 
 
 class MinkowskiLinear(nn.Module):
+    _osb_me_op = True      # an operator of this package (fast_eval.py looks for the module that CALLS them)
     def __init__(self, in_features, out_features, bias=True):
         super().__init__()
         self.linear = nn.Linear(in_features, out_features, bias=bias)
@@ -403,6 +449,7 @@ class MinkowskiLinear(nn.Module):
 
 
 class _PoolBase(nn.Module):
+    _osb_me_op = True      # an operator of this package (fast_eval.py looks for the module that CALLS them)
     def __init__(self, kernel_size, stride=1, dilation=1, kernel_generator=None, dimension=None):
         super().__init__()
         if dimension != 3:
@@ -434,6 +481,7 @@ class MinkowskiAvgPooling(_PoolBase):
 
 
 class MinkowskiGlobalMaxPooling(nn.Module):
+    _osb_me_op = True      # an operator of this package (fast_eval.py looks for the module that CALLS them)
     def __init__(self, dimension=None, **kw):
         super().__init__()
 
