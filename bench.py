@@ -204,8 +204,131 @@ def run_reference(args, rank):
     print(json.dumps(line))
 
 
+def run_distill(args, rank, local, world):
+    """`--workload config3_distill`: one step of run/distill.py:311-334 per rank -- random integer translation, forward with
+    BatchNorm in train mode, row select by the supervision mask, cosine distillation loss against fp16 fused features,
+    backward (dgrad + wgrad on tensor cores), DDP gradient all-reduce over NCCL (world > 1), Adam step.  One ScanNet-shaped
+    scene per GPU (batch_size 8 over 8 GPUs, config/scannet/ours_openseg.yaml:14-16), MinkUNet18A unless --arch says otherwise,
+    M = 20,000 supervised voxels per scene (scripts/feature_fusion/scannet_openseg.py:145-147)."""
+    import torch.distributed as dist
+    from openscene_b200 import _cabi, distill, synth
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    arch = args.arch if args.arch != 'MinkUNet34C' or os.environ.get('OSB_DISTILL_34C') else 'MinkUNet18A'
+    coords_np = synth.scene('config2_200k', seed=rank)
+    n0 = len(coords_np)
+    g = torch.Generator().manual_seed(100 + rank)
+    m_sup = min(20_000, n0)
+    mask_h = torch.zeros(n0, dtype=torch.bool)
+    mask_h[torch.randperm(n0, generator=g)[:m_sup]] = True
+    feat3d_h = (torch.randn(m_sup, 768, generator=g) * 0.3).half().pin_memory()
+    coords_h = torch.from_numpy(coords_np).pin_memory()
+    feats_h = torch.ones(n0, 3).pin_memory()
+    mask_h = mask_h.pin_memory()
+    torch.manual_seed(0)
+    model = synth.build_model(arch, 768, seed=0).train().to(dev)
+    ddp = distill.wrap_ddp(model, dev)
+    opt = torch.optim.Adam(ddp.parameters(), lr=1e-4)                  # run/distill.py:141
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    loss_host = torch.zeros(1).pin_memory()
+
+    def step(sync=True):
+        """H2D of the batch, the step, D2H of the loss: the call a user of run/distill.py makes per iteration."""
+        c, f = coords_h.to(dev, non_blocking=True), feats_h.to(dev, non_blocking=True)
+        t3, mk = feat3d_h.to(dev, non_blocking=True), mask_h.to(dev, non_blocking=True)
+        ctx = ddp.no_sync() if (not sync and world > 1) else _null()
+        with ctx:
+            loss = distill.distill_step(ddp, opt, c, f, t3, mk, 'cosine', translate=True)
+        loss_host.copy_(loss.reshape(1), non_blocking=True)
+        return loss
+
+    def timed(fn, k):
+        import gc
+        gc.collect(); gc.disable()
+        evs = []
+        for _ in range(k):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        gc.enable()
+        ts = sorted(a.elapsed_time(b) for a, b in evs)
+        return sum(ts), {'min': ts[0], 'median': ts[len(ts) // 2], 'max': ts[-1]}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local, dev) if rank == 0 else None
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    l0 = _cabi.lib().osb_launch_count()
+    if sampler:
+        sampler.nvml_reasons(); torch.cuda.synchronize()
+    ms, stats = timed(step, args.steps)
+    if sampler:
+        sampler.sample(); sampler.nvml_reasons()
+    launches = _cabi.lib().osb_launch_count() - l0
+    barrier()
+    ms_nosync = None
+    if world > 1:                                                      # the same step without the gradient all-reduce
+        for _ in range(2):
+            step(sync=False)
+        barrier()
+        ms_nosync, _ = timed(lambda: step(sync=False), max(3, args.steps // 2))
+        ms_nosync /= max(3, args.steps // 2)
+        barrier()
+    stats_t = torch.tensor([ms, float(n0)], dtype=torch.float64, device=dev)
+    if world > 1:
+        allst = [torch.zeros_like(stats_t) for _ in range(world)]
+        dist.all_gather(allst, stats_t)
+        allst = torch.stack(allst).cpu()
+    else:
+        allst = stats_t.cpu().unsqueeze(0)
+    t_all, total_vox = float(allst[:, 0].max()), float(allst[:, 1].sum())
+    if rank == 0:
+        n_par = sum(p.numel() for p in model.parameters())
+        value = total_vox * args.steps / (t_all / 1e3)
+        line = {'metric': 'voxels/s distillation step (fwd + cosine loss + bwd + Adam)', 'value': value, 'unit': 'voxels/s',
+                'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': t_all / args.steps,
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': 'bf16x3 (split fp32 operands, fp32 accumulate); wgrad bf16x4', 'data': 'synthetic',
+                'config': {'workload': f'config3_distill: one config2_200k scene ({n0} voxels) per GPU, {arch}, 768-d head, '
+                                       f'{m_sup} supervised voxels, cosine loss, Adam, DDP/NCCL gradient all-reduce of '
+                                       f'{n_par * 4 / 1e6:.0f} MB', 'points': 'stride-1 voxels fed to SparseTensor',
+                           'l2': 'flushed (256 MiB memset) before every timed step'},
+                'e2e': {'value': value, 'unit': 'voxels/s', 'ms_per_step': t_all / args.steps,
+                        'h2d_bytes_per_step': int(coords_h.numel() * 4 + feats_h.numel() * 4 + feat3d_h.numel() * 2 + mask_h.numel()),
+                        'd2h_bytes_per_step': 4, 'note': 'the timed step IS the end-to-end call: H2D of the batch and D2H of the loss inside'},
+                'gpu_launches': int(launches), 'clocks': sampler.stop() if sampler else None, 'step_ms_stats': stats,
+                'allreduce': None if ms_nosync is None else {
+                    'ms_per_step_with': t_all / args.steps, 'ms_per_step_without': ms_nosync,
+                    'exposed_ms': t_all / args.steps - ms_nosync, 'bytes': n_par * 4,
+                    'note': 'rank-0 step time under DDP.no_sync() vs the DDP step; the difference is the all-reduce time not hidden '
+                            'behind backward'}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+class _null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
 def main():
     args = parse()
+    if args.workload == 'config3_distill' and args.impl != 'reference':
+        return run_distill(args, int(os.environ.get('RANK', 0)), int(os.environ.get('LOCAL_RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)))
     if args.k_text is None:
         args.k_text = {'config4_matterport': 160, 'config5_lidar': 16}.get(args.workload, 20)
     if args.match is None:

@@ -130,6 +130,14 @@ int osb_conv_fwd_f32(const float *in, int64_t ld_in, const int32_t *nbr, int64_t
 int osb_conv_wgrad_f32(const float *in, const int32_t *nbr, int64_t n_out, int32_t K, const float *gout,
                        int32_t cin, int32_t cout, float *gw, void *stream);
 
+/* Weight gradient on tensor cores (run/distill.py:333): gw[k] = sum_o x[nbr[k][o],:]^T gout[o,:] with both operands in the
+ * split layout (x_split [n_in, cin], gout_split [n_out, cout]); gw fp32 [K,cin,cout] is overwritten.  Every product is the
+ * full (hi+lo)(hi+lo) expansion on kind::f16 MMAs with fp32 accumulation; partial tiles are reduced in a fixed order
+ * (bit-reproducible, no atomics).  ws: osb_conv_wgrad_tc_workspace_bytes(...) bytes. */
+size_t osb_conv_wgrad_tc_workspace_bytes(int64_t n_out, int32_t K, int32_t cin, int32_t cout);
+int osb_conv_wgrad_tc(const void *x_split, int32_t cin, int64_t n_in, const int32_t *nbr, int64_t n_out, int32_t K,
+                      const void *gout_split, int32_t cout, float *gw, void *ws, size_t ws_bytes, void *stream);
+
 /* Tensor-core path (tcgen05, bf16x3 split-fp32 operands, fp32 accumulation in TMEM).
  *
  * Activation "split" layout: a row of C channels (C % 32 == 0) is 4*C bytes; every 32-channel block is

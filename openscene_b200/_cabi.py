@@ -30,6 +30,8 @@ SIGNATURES = {
     'osb_kernel_map_transpose': (c_int, [P, I64, I32, P, I64, P]),
     'osb_conv_fwd_f32': (c_int, [P, I64, P, I64, I32, P, I32, I32, I32, P, P]),
     'osb_conv_wgrad_f32': (c_int, [P, P, I64, I32, P, I32, I32, P, P]),
+    'osb_conv_wgrad_tc_workspace_bytes': (SZ, [I64, I32, I32, I32]),
+    'osb_conv_wgrad_tc': (c_int, [P, I32, I64, P, I64, I32, P, I32, P, P, SZ, P]),
     'osb_conv_packed_weight_bytes': (SZ, [I32, I32, I32]),
     'osb_conv_pack_weights': (c_int, [P, I32, I32, I32, I32, P, P]),
     'osb_conv_tc_workspace_bytes': (SZ, [I64, I32, I32, I32]),

@@ -206,10 +206,10 @@ k_conv_chain(const ConvDesc *__restrict__ descs, int n_layers, unsigned *gbar, i
         (void)m; (void)nti;
         const uint32_t buf = n_item & 1u;
         const bool mine = mi < nsub;
-        if (mine) {
-          mbar_wait(accEmpty + 8 * buf, ((n_item >> 1) & 1u) ^ 1u);       // the epilogue drained this buffer
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        }
+        // Both issuers follow the full protocol of every item, also the one without a sub-tile of its own (single-sub-tile
+        // items): its arrivals on emptyB / accFull may only happen in the phase they belong to, i.e. after the same waits.
+        mbar_wait(accEmpty + 8 * buf, ((n_item >> 1) & 1u) ^ 1u);         // the epilogue drained this buffer
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t dcol = tmem_base + buf * 256u + (uint32_t)mi * 128u;
         for (int t = t_begin; t < t_end; ++t) {
           if (mine) {
@@ -235,8 +235,9 @@ k_conv_chain(const ConvDesc *__restrict__ descs, int n_layers, unsigned *gbar, i
               umma_commit(emptyA + 8 * sl);                                 // row slot free when these MMAs retire
               umma_commit(emptyB + 8 * b_slot);                             // weight slot: one arrival per issuer
             }
-          } else if (lane == 0) {
-            mbar_arrive(emptyB + 8 * b_slot);                               // nothing of mine reads this weight tile
+          } else {
+            mbar_wait(fullB + 8 * b_slot, b_phase);                         // stay in step with the slot's phase ...
+            if (lane == 0) mbar_arrive(emptyB + 8 * b_slot);                // ... nothing of mine reads this weight tile
           }
           __syncwarp();
           a_slot += (uint32_t)nsub;

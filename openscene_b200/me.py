@@ -257,29 +257,33 @@ def _tc_ok(cin, cout, K):
     return cin % 32 == 0 and cout % 32 == 0 and K <= 32 and _module_tc_enabled()
 
 
-def _conv_tc_f32(x, kmap, wpack, cin, cout, K, n_out):
-    """fp32 rows in, fp32 rows out through the tcgen05 kernel (bf16x3 split operands)."""
+def _conv_tc_split(xs, kmap, wpack, cin, cout, K, n_out):
+    """split rows in, fp32 rows out through the tcgen05 kernel (bf16x3 split operands)."""
     from . import tc
-    xs = tc.to_split(x)
     nbr = kmap.nbr if kmap is not None else None
     return tc.conv_tc(xs, cin, None, 0, nbr, n_out, K, wpack, cout, out_split=False, out_f32=True)[1]
 
 
 class SparseConvFunction(torch.autograd.Function):
     """Forward / dgrad / wgrad of the generalised sparse convolution on libosb200 kernels
-    (replaces MinkowskiConvolutionFunction / ...TransposeFunction inside MinkowskiEngine).
-    Forward and dgrad run on the tcgen05 kernel when the channel counts are multiples of 32 (dgrad = the same
-    kernel on the transposed map with W^T packed); wgrad and odd shapes use the exact-fp32 CUDA-core kernels."""
+    (replaces MinkowskiConvolutionFunction / ...TransposeFunction inside MinkowskiEngine; run/distill.py:321,333).
+    With channel counts that are multiples of 32 all three run on tensor cores: forward and dgrad on the tcgen05
+    convolution kernel (dgrad = the same kernel on the transposed map with W^T packed), wgrad on csrc/conv_wgrad_tc.cu.
+    The input is saved in the split-bf16 layout the kernels read (the conversion is paid once, in forward); packed weights
+    are memoised on the parameter's version counter.  Odd shapes use the exact-fp32 CUDA-core kernels."""
 
     @staticmethod
     def forward(ctx, x, w3, kmap, n_out):
         ctx.kmap, ctx.n_in = kmap, x.shape[0]
-        ctx.save_for_backward(x, w3)
         K, cin, cout = w3.shape
+        ctx.tc = bool(_tc_ok(cin, cout, K) and x.dtype == torch.float32)
         with torch.cuda.device(x.device):
-            if _tc_ok(cin, cout, K) and x.dtype == torch.float32:
+            if ctx.tc:
                 from . import tc
-                return _conv_tc_f32(x.contiguous(), kmap, tc.pack_weights(w3), cin, cout, K, n_out)
+                xs = tc.to_split(x.contiguous())
+                ctx.save_for_backward(xs, w3)
+                return _conv_tc_split(xs, kmap, tc.packed_weights_cached(w3), cin, cout, K, n_out)
+            ctx.save_for_backward(x, w3)
             return _conv_raw(x, kmap, w3, n_out)
 
     @staticmethod
@@ -289,14 +293,23 @@ class SparseConvFunction(torch.autograd.Function):
         gout = gout.contiguous()
         gx = gw = None
         K, cin, cout = w3.shape
-        with torch.cuda.device(x.device):
+        with torch.cuda.device(gout.device):
+            if ctx.tc and gout.dtype == torch.float32:
+                from . import tc
+                gs = tc.to_split(gout)                                    # shared by dgrad and wgrad
+                if ctx.needs_input_grad[0]:
+                    kt = kmap.transposed() if kmap is not None else None
+                    gx = _conv_tc_split(gs, kt, tc.packed_weights_cached(w3, transpose_w=True), cout, cin, K, ctx.n_in)
+                if ctx.needs_input_grad[1]:
+                    nbr = kmap.nbr if kmap is not None else None
+                    gw = tc.conv_wgrad_tc(x, cin, ctx.n_in, nbr, gout.shape[0], K, gs, cout)
+                return gx, gw, None, None
+            if ctx.tc:                                                    # saved input is in the split layout
+                from . import tc
+                x = tc.from_split(x, cin)
             if ctx.needs_input_grad[0]:
                 kt = kmap.transposed() if kmap is not None else None
-                if _tc_ok(cin, cout, K) and gout.dtype == torch.float32:
-                    from . import tc
-                    gx = _conv_tc_f32(gout, kt, tc.pack_weights(w3, transpose_w=True), cout, cin, K, ctx.n_in)
-                else:
-                    gx = _conv_raw(gout, kt, w3, ctx.n_in, transpose_w=True)
+                gx = _conv_raw(gout, kt, w3, ctx.n_in, transpose_w=True)
             if ctx.needs_input_grad[1]:
                 gw = torch.empty_like(w3)
                 nbr = kmap.nbr if kmap is not None else None

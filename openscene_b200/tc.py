@@ -60,6 +60,32 @@ def conv_tc(src0, c0, src1, c1, nbr, n_out, K, wpack, cout, scale=None, shift=No
     return os_, of_
 
 
+def conv_wgrad_tc(x_split, cin, n_in, nbr, n_out, K, gout_split, cout):
+    """gw fp32 [K, cin, cout] = sum_o x[nbr[k][o]]^T gout[o] on tensor cores (csrc/conv_wgrad_tc.cu)."""
+    dev = x_split.device
+    gw = torch.empty((K, cin, cout), dtype=torch.float32, device=dev)
+    ws_bytes = C.lib().osb_conv_wgrad_tc_workspace_bytes(n_out, K, cin, cout)
+    ws = _workspace(dev, ws_bytes)
+    C.call('osb_conv_wgrad_tc', C.ptr(x_split), cin, n_in, C.ptr(nbr), n_out, K, C.ptr(gout_split), cout, C.ptr(gw), C.ptr(ws),
+           ws_bytes, C.stream_ptr())
+    return gw
+
+
+_PACK_CACHE = {}
+
+
+def packed_weights_cached(w3, transpose_w=False):
+    """``pack_weights`` memoised on (storage address, version counter): the packed operand is rebuilt only when the
+    parameter was written (optimizer step, load_state_dict), not on every forward / backward."""
+    key = (w3.data_ptr(), w3._version, bool(transpose_w), tuple(w3.shape))
+    hit = _PACK_CACHE.get(key)
+    if hit is None:
+        if len(_PACK_CACHE) > 1024:                     # stale versions of trained weights: drop everything, refill lazily
+            _PACK_CACHE.clear()
+        hit = _PACK_CACHE[key] = pack_weights(w3, transpose_w)
+    return hit
+
+
 def conv_stem(x, coords, slots, cap, ks, step, w3, scale=None, shift=None, relu=False, out_split=True, out_f32=False):
     n, cin = x.shape
     cout = w3.shape[2]
