@@ -39,6 +39,7 @@ constexpr int CH_A_BYTES = CH_M * 128;           // one row slot: 128 rows x one
 constexpr int CH_STG_BYTES = 8 * 4096;           // epilogue staging: 8 warps x (32 rows x 128 B)
 constexpr int CH_SS_FLOATS = 768;                // folded BN constants kept in shared memory per layer (scale | shift)
 constexpr int CH_MAX_SA = 12, CH_MAX_SB = 4;
+constexpr int CH_PEND = 3;                       // row slots a producer thread keeps in flight before it announces the oldest
 constexpr int CH_DESC_WORDS = 48;                // sizeof(ConvDesc) / 4
 
 struct __align__(16) ConvDesc {
@@ -100,6 +101,10 @@ __device__ __forceinline__ void grid_barrier(unsigned *gbar, unsigned &gen) {
   __syncthreads();
 }
 
+// per-role cycle accounting (tuning; active only when a clock buffer is given): dbg_clock[cta*32 + slot]
+#define CH_PROF_BEGIN() const long long _t0 = prof ? clock64() : 0
+#define CH_PROF_END(var) do { if (prof) var += clock64() - _t0; } while (0)
+
 // ------------------------------------------------------------------------------------ the kernel
 __global__ void __launch_bounds__(CH_THREADS, 1)
 k_conv_chain(const ConvDesc *__restrict__ descs, int n_layers, unsigned *gbar, int sa, int sb, int bslot, int flags,
@@ -115,13 +120,15 @@ k_conv_chain(const ConvDesc *__restrict__ descs, int n_layers, unsigned *gbar, i
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (flags & 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  if (dbg_clock && tid == 0) dbg_clock[blockIdx.x * 8 + 0] = clock64();
+  const bool prof = dbg_clock != nullptr;
+  long long pw0 = 0, pw1 = 0, pw2 = 0, pt = 0;     // cycles in this role's waits (up to three kinds) and in its loop
+  if (dbg_clock && tid == 0) dbg_clock[blockIdx.x * 32 + 0] = clock64();
   const uint32_t fullA = smem_u32(bars), emptyA = smem_u32(bars + 12);
   const uint32_t fullB = smem_u32(bars + 24), emptyB = smem_u32(bars + 28);
   const uint32_t accFull = smem_u32(bars + 32), accEmpty = smem_u32(bars + 34);
 
   if (tid == 0) {
-    for (int s = 0; s < sa; ++s) { mbar_init(fullA + 8 * s, (flags & 0x8000) ? 4 : 128); mbar_init(emptyA + 8 * s, 1); }
+    for (int s = 0; s < sa; ++s) { mbar_init(fullA + 8 * s, (flags & 0x10000) ? 128 : 4); mbar_init(emptyA + 8 * s, 1); }
     for (int s = 0; s < sb; ++s) { mbar_init(fullB + 8 * s, 1); mbar_init(emptyB + 8 * s, 2); }   // emptyB: one arrival per issuer
     for (int b = 0; b < 2; ++b) { mbar_init(accFull + 8 * b, 2); mbar_init(accEmpty + 8 * b, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -138,10 +145,11 @@ k_conv_chain(const ConvDesc *__restrict__ descs, int n_layers, unsigned *gbar, i
   // Everything above touched no data of an earlier kernel in the stream; from here on we read activations.
   if (flags & 1) asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t tmem_base = s_misc[0];
-  if (dbg_clock && tid == 0) dbg_clock[blockIdx.x * 8 + 1] = clock64();
+  if (dbg_clock && tid == 0) dbg_clock[blockIdx.x * 32 + 1] = clock64();
 
   // pipeline state of this thread's role; persists over items and layers
   uint32_t a_slot = 0, a_phase = 0, b_slot = 0, b_phase = 0, n_item = 0;
+  uint32_t arr_slot = 0, n_pend = 0;               // A producers: oldest slot not yet announced, slots issued but not announced
 
   for (int L = 0; L < n_layers; ++L) {
     __syncthreads();                                   // every role is done with the previous layer (and with s_desc)
@@ -176,12 +184,13 @@ k_conv_chain(const ConvDesc *__restrict__ descs, int n_layers, unsigned *gbar, i
           t_begin = min(z * d.stages_per_split, T), t_end = min(t_begin + d.stages_per_split, T);              \
           (_n = nsub, true))
 
+    const long long _role_t0 = prof ? clock64() : 0;
     if (warp == 0) {
       // ============================ weight tiles ====================================
       CH_FOR_ITEMS() {
         (void)m;
         for (int t = t_begin; t < t_end; ++t) {
-          mbar_wait(emptyB + 8 * b_slot, b_phase ^ 1);
+          { CH_PROF_BEGIN(); mbar_wait(emptyB + 8 * b_slot, b_phase ^ 1); CH_PROF_END(pw0); }
           if (elect_one()) {
             const uint32_t fb = fullB + 8 * b_slot;
             if (flags & 0x200) {                      // tuning: no weight loads
@@ -208,16 +217,16 @@ k_conv_chain(const ConvDesc *__restrict__ descs, int n_layers, unsigned *gbar, i
         const bool mine = mi < nsub;
         // Both issuers follow the full protocol of every item, also the one without a sub-tile of its own (single-sub-tile
         // items): its arrivals on emptyB / accFull may only happen in the phase they belong to, i.e. after the same waits.
-        mbar_wait(accEmpty + 8 * buf, ((n_item >> 1) & 1u) ^ 1u);         // the epilogue drained this buffer
+        { CH_PROF_BEGIN(); mbar_wait(accEmpty + 8 * buf, ((n_item >> 1) & 1u) ^ 1u); CH_PROF_END(pw2); }   // the epilogue drained this buffer
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t dcol = tmem_base + buf * 256u + (uint32_t)mi * 128u;
         for (int t = t_begin; t < t_end; ++t) {
           if (mine) {
             uint32_t sl = a_slot + (uint32_t)mi, ph = a_phase;             // my row slot of this stage
             if (sl >= (uint32_t)sa) { sl -= (uint32_t)sa; ph ^= 1u; }
-            mbar_wait(fullB + 8 * b_slot, b_phase);
-            mbar_wait(fullA + 8 * sl, ph);
-            if (!(flags & 0x1000)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) writes -> UMMA reads
+            { CH_PROF_BEGIN(); mbar_wait(fullB + 8 * b_slot, b_phase); CH_PROF_END(pw0); }
+            { CH_PROF_BEGIN(); mbar_wait(fullA + 8 * sl, ph); CH_PROF_END(pw1); }
+            if (flags & 0x10000) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // legacy completion: fence on the consumer side
             if (!(flags & 0x2000)) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (flags & 0x4000) {                     // tuning: plain arrivals instead of tcgen05.commit (only without MMAs)
               if (lane == 0) { mbar_arrive(emptyA + 8 * sl); mbar_arrive(emptyB + 8 * b_slot); }
@@ -271,10 +280,15 @@ k_conv_chain(const ConvDesc *__restrict__ descs, int n_layers, unsigned *gbar, i
         int k_cur = t_begin / nb;
         if (t_begin < t_end) fetch(k_cur, nxt);
         for (int t = t_begin; t < t_end;) {
+          {
+            CH_PROF_BEGIN();
 #pragma unroll
-          for (int s = 0; s < 2; ++s)
+            for (int s = 0; s < 2; ++s)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) cur[s][i] = nxt[s][i];
+              for (int i = 0; i < 8; ++i) cur[s][i] = nxt[s][i];
+            if (prof) { int acc_ = 0; for (int s = 0; s < 2; ++s) for (int i = 0; i < 8; ++i) acc_ += cur[s][i]; if (acc_ == 0x7fffffff) pw2 += 1; }   // force the loads to land here
+            CH_PROF_END(pw1);
+          }
           const int t_next_k = min((k_cur + 1) * nb, t_end);                // first stage of the next offset
           if (t_next_k < t_end) fetch(k_cur + 1, nxt);                      // one offset ahead: latency behind this offset's copies
           for (; t < t_next_k; ++t) {
@@ -284,7 +298,7 @@ k_conv_chain(const ConvDesc *__restrict__ descs, int n_layers, unsigned *gbar, i
             const int64_t row_bytes = (int64_t)(first ? d.nb0 : d.nb1) * 128;
             const int col_byte = (first ? cb : cb - d.nb0) * 128 + j * 16;
             for (int s = 0; s < nsub; ++s) {
-              mbar_wait(emptyA + 8 * a_slot, a_phase ^ 1);
+              { CH_PROF_BEGIN(); mbar_wait(emptyA + 8 * a_slot, a_phase ^ 1); CH_PROF_END(pw0); }
               const uint32_t a_dst = smem_u32(smem + a_slot * CH_A_BYTES) + (w * 32 + q) * 128;
               if (!(flags & 0x100)) {                 // tuning: bit 8 = no row copies
 #pragma unroll
@@ -296,12 +310,35 @@ k_conv_chain(const ConvDesc *__restrict__ descs, int n_layers, unsigned *gbar, i
                   cp_async16(a_dst + i * 512 + ((j ^ m7) << 4), sp, valid ? 16u : 0u);      // size 0 -> zero fill
                 }
               }
-              if (flags & 0x8000) { __syncwarp(); if (lane == 0) mbar_arrive(fullA + 8 * a_slot); }   // tuning: one arrival per warp
-              else cp_async_arrive_noinc(fullA + 8 * a_slot);
+              if (flags & 0x10000) {                  // first-generation completion: 128 self-tracking arrivals per slot
+                cp_async_arrive_noinc(fullA + 8 * a_slot);
+              } else {
+                // Completion on the PRODUCER side, CH_PEND slots behind the issue front: wait for this thread's copies of
+                // the oldest pending slot, make them visible to the async proxy (the tensor core reads shared memory through
+                // it), one arrival per warp.  The MMA issuer's per-slot critical path is then wait -> MMAs -> commit.
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                if (++n_pend > CH_PEND) {
+                  asm volatile("cp.async.wait_group %0;" ::"n"(CH_PEND) : "memory");
+                  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                  __syncwarp();
+                  if (lane == 0) mbar_arrive(fullA + 8 * arr_slot);
+                  if (++arr_slot == (uint32_t)sa) arr_slot = 0;
+                  --n_pend;
+                }
+              }
               if (++a_slot == (uint32_t)sa) { a_slot = 0; a_phase ^= 1; }
             }
           }
           ++k_cur;
+        }
+      }
+      if (!(flags & 0x10000)) {                       // drain: the last slots of the layer
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        for (; n_pend > 0; --n_pend) {
+          if (lane == 0) mbar_arrive(fullA + 8 * arr_slot);
+          if (++arr_slot == (uint32_t)sa) arr_slot = 0;
         }
       }
     } else if (warp >= 8) {
@@ -315,7 +352,7 @@ k_conv_chain(const ConvDesc *__restrict__ descs, int n_layers, unsigned *gbar, i
       auto sts128 = [](uint32_t a, uint4 v) { asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); };
       CH_FOR_ITEMS() {
         if ((n_item & 1u) != (uint32_t)eg) { ++n_item; continue; }
-        mbar_wait(accFull + 8 * eg, (n_item >> 1) & 1u);
+        { CH_PROF_BEGIN(); mbar_wait(accFull + 8 * eg, (n_item >> 1) & 1u); CH_PROF_END(pw0); }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int s = 0; s < nsub; ++s) {
           const int64_t wrow0 = (int64_t)(m + s) * CH_M + q * 32;        // first global row of this warp
@@ -431,6 +468,7 @@ k_conv_chain(const ConvDesc *__restrict__ descs, int n_layers, unsigned *gbar, i
       }
     }
 #undef CH_FOR_ITEMS
+    if (prof) pt += clock64() - _role_t0;
 
     if (d.nsplit > 1) {
       // ---- split-K: every partial is in global memory after this barrier; reduce + epilogue by all threads of the grid
@@ -479,7 +517,13 @@ k_conv_chain(const ConvDesc *__restrict__ descs, int n_layers, unsigned *gbar, i
     }
   }
 
-  if (dbg_clock && tid == 0) dbg_clock[blockIdx.x * 8 + 2] = clock64();
+  if (dbg_clock && tid == 0) dbg_clock[blockIdx.x * 32 + 2] = clock64();
+  if (dbg_clock && lane == 0 && (warp == 0 || warp == 1 || warp == 2 || warp == 4 || warp == 8 || warp == 12)) {
+    // rows of 4: [wait kind 0, wait kind 1, wait kind 2, role loop total]; B producer 4.., issuer0 8.., issuer1 12.., A producer 16.., epilogue0 20.., epilogue1 24..
+    const int base = warp == 0 ? 4 : warp == 1 ? 8 : warp == 2 ? 12 : warp == 4 ? 16 : warp == 8 ? 20 : 24;
+    long long *o = dbg_clock + blockIdx.x * 32 + base;
+    o[0] = pw0; o[1] = pw1; o[2] = pw2; o[3] = pt;
+  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
@@ -548,7 +592,8 @@ static int g_chain_nsub = 2;             // tuning: 1 = never pair sub-tiles
 static int g_chain_grid = 0;             // tuning: CTAs per launch (0 = one per SM)
 static int g_chain_sa = 0, g_chain_sb = 0;   // tuning: ring depths (0 = as many row slots as fit / 3 or 2 weight slots)
 static long long *g_chain_dbg_clock = nullptr;
-static int g_chain_dbg_skip = 0;         // tuning: bit0 no row copies, bit1 no weight loads, bit2 no MMAs, bit3 no stores
+static int g_chain_dbg_skip = 0;         // tuning: bit0 no row copies, bit1 no weight loads, bit2 no MMAs, bit3 no stores,
+                                         // bit5 no tcgen05 fence, bit6 plain arrivals for commits, bit8 legacy (consumer-side) completion
 
 int osb_tuning_set(const char *name, int64_t value) {
   const std::string n(name ? name : "");
@@ -636,7 +681,7 @@ int osb_conv_chain_launch(const void *descs_dev, const void *descs_host, int32_t
   int sa = (227 * 1024 - fixed - sb * bslot) / CH_A_BYTES;
   if (g_chain_sa > 0) sa = std::min(sa, g_chain_sa);
   sa = std::min(sa, CH_MAX_SA);
-  OSB_CHECK(sa >= 2, "osb_conv_chain_launch: shared memory does not hold two row slots");
+  OSB_CHECK(sa >= CH_PEND + 2, "osb_conv_chain_launch: shared memory does not hold %d row slots", CH_PEND + 2);
   const size_t smem_bytes = (size_t)sa * CH_A_BYTES + (size_t)sb * bslot + fixed;
   OSB_SMEM_ATTR_ONCE(k_conv_chain, 227 * 1024);
   const int grid = osb_conv_chain_grid();

@@ -41,21 +41,20 @@ def timed(fn, reps=20):
 print(f'# {workload} n={n} {cin}->{cout} k={ks}')
 print(f'legacy k_conv_tc                         {timed(lambda: tc.conv_tc(x, cin, None, 0, nbr, n, ks ** 3, wp, cout)):8.1f} us')
 SETS = [
-    ('chain default', {}),
+    ('chain default (producer-side completion)', {}),
+    ('legacy completion: noinc arrivals + consumer fence (0x100)', {'chain_dbg_skip': 0x100}),
     ('nsub=1', {'chain_nsub': 1}),
     ('no A,B,MMA (0x7)', {'chain_dbg_skip': 0x7}),
-    ('0x7 + no fence.proxy.async (0x17)', {'chain_dbg_skip': 0x17}),
-    ('0x7 + no proxy/tcgen05 fences (0x37)', {'chain_dbg_skip': 0x37}),
-    ('0x37 + plain arrives for commits (0x77)', {'chain_dbg_skip': 0x77}),
-    ('0x77 + one producer arrival per warp (0xf7)', {'chain_dbg_skip': 0xf7}),
-    ('0x7 + one producer arrival per warp (0x87)', {'chain_dbg_skip': 0x87}),
+    ('0x7 + no tcgen05 fence (0x27)', {'chain_dbg_skip': 0x27}),
+    ('0x27 + plain arrives for commits (0x67)', {'chain_dbg_skip': 0x67}),
+    ('0x7 legacy completion (0x107)', {'chain_dbg_skip': 0x107}),
     ('no A,B (0x3)', {'chain_dbg_skip': 0x3}),
     ('no A (0x1)', {'chain_dbg_skip': 0x1}),
-    ('full, no fence.proxy.async (0x10) [wrong results]', {'chain_dbg_skip': 0x10}),
+    ('no B (0x2)', {'chain_dbg_skip': 0x2}),
     ('no stores (0x8)', {'chain_dbg_skip': 0x8}),
-    ('sa=4', {'chain_sa': 4}),
-    ('sa=6', {'chain_sa': 6}),
-    ('grid=296?', {}),
+    ('sa=5', {'chain_sa': 5}),
+    ('sa=7', {'chain_sa': 7}),
+    ('end', {}),
 ]
 for name, knobs in SETS[:-1]:
     for k_, v_ in (('chain_dbg_skip', 0), ('chain_nsub', 2), ('chain_sa', 0)):
