@@ -41,16 +41,14 @@ def timed(fn, reps=20):
 print(f'# {workload} n={n} {cin}->{cout} k={ks}')
 print(f'legacy k_conv_tc                         {timed(lambda: tc.conv_tc(x, cin, None, 0, nbr, n, ks ** 3, wp, cout)):8.1f} us')
 SETS = [
-    ('chain default (producer-side completion)', {}),
-    ('legacy completion: noinc arrivals + consumer fence (0x100)', {'chain_dbg_skip': 0x100}),
+    ('chain default (noinc arrivals, consumer-side fence)', {}),
+    ('producer-side completion (0x100)', {'chain_dbg_skip': 0x100}),
     ('nsub=1', {'chain_nsub': 1}),
     ('no A,B,MMA (0x7)', {'chain_dbg_skip': 0x7}),
-    ('0x7 + no tcgen05 fence (0x27)', {'chain_dbg_skip': 0x27}),
-    ('0x27 + plain arrives for commits (0x67)', {'chain_dbg_skip': 0x67}),
-    ('0x7 legacy completion (0x107)', {'chain_dbg_skip': 0x107}),
     ('no A,B (0x3)', {'chain_dbg_skip': 0x3}),
     ('no A (0x1)', {'chain_dbg_skip': 0x1}),
     ('no B (0x2)', {'chain_dbg_skip': 0x2}),
+    ('no MMA (0x4)', {'chain_dbg_skip': 0x4}),
     ('no stores (0x8)', {'chain_dbg_skip': 0x8}),
     ('sa=5', {'chain_sa': 5}),
     ('sa=7', {'chain_sa': 7}),
