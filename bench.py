@@ -442,6 +442,38 @@ def main():
     ms_e2e = timed(step_e2e, args.steps, tag='e2e')
     barrier()
 
+    # ---- the same step from RAW POINTS (dataset/voxelizer.py on the device): H2D of float32 points, voxelise (affine, floor,
+    #      FNV key, first-occurrence unique), network, matching with the voxel->point expansion fused in, D2H of per-point labels
+    ms_points, n_pts = None, 0
+    if not args.modules:
+        from openscene_b200.voxelize import voxelize_points
+        pts_np, vsize = synth.scene_points(args.workload, seed=rank)
+        n_pts = len(pts_np)
+        pts_host = torch.from_numpy(pts_np.astype(np.float32)).pin_memory()
+        Mv = np.eye(4); Mv[0, 0] = Mv[1, 1] = Mv[2, 2] = 1.0 / vsize
+        plabel_host = torch.empty(n_pts, dtype=torch.int64).pin_memory()
+
+        def step_points():
+            p = pts_host.to(dev, non_blocking=True)
+            cv, inds, inv, _ = voxelize_points(p, Mv)                 # SYNC inside: the voxel count comes back to the host
+            c4 = torch.zeros((cv.shape[0], 4), dtype=torch.int32, device=dev)
+            c4[:, 1:] = cv
+            out = eng(c4, torch.ones(cv.shape[0], 3, device=dev))
+            if args.match == 'ensemble':
+                _, lab, _, _ = matching.match_ensemble(out, feat2d[:cv.shape[0]], inv, text)
+            else:
+                _, lab, _ = matching._scores(out, inv, text, normalize=True, want_scores=False)
+            plabel_host.copy_(lab, non_blocking=True)
+        try:
+            for _ in range(2):
+                step_points()
+            barrier()
+            ms_points = timed(step_points, min(args.steps, 20)) / min(args.steps, 20)
+        except Exception as e:                                        # noqa: BLE001  (extra measurement: never fail the headline)
+            ms_points = None
+            print(f'[bench] e2e_points skipped: {e}', file=sys.stderr)
+        barrier()
+
     # ---- optional re-associated head (not the headline: the 768-d features are not materialised) -----
     ms_folded = None
     if not args.modules:
@@ -506,6 +538,11 @@ def main():
                     'h2d_bytes_per_step': int(coords_host.numel() * 4 + feats_host.numel() * 4), 'd2h_bytes_per_step': int(n0 * 8)},
             'gpu_launches': int(launches), 'clocks': clocks, 'step_ms_stats': step_stats,
         }
+        if ms_points is not None:
+            line['e2e_points'] = {'ms_per_step': ms_points, 'points_per_s': n_pts / (ms_points / 1e3), 'voxels_per_s': n0 / (ms_points / 1e3),
+                                  'n_points': n_pts, 'h2d_bytes_per_step': n_pts * 12, 'd2h_bytes_per_step': n_pts * 8,
+                                  'note': 'rank 0: float32 points from pinned host memory -> osb_voxelize -> engine -> matching through '
+                                          'inds_reverse -> int64 labels per POINT back to pinned host memory'}
         if ms_folded is not None:
             line['extra'] = {'folded_head_ms_per_step': ms_folded,
                              'note': 'optional engine.forward_scores: final 1x1x1 conv re-associated with the text matrix '

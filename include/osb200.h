@@ -187,8 +187,8 @@ int osb_convtr_fwd_tc(const void *src, int32_t cin, int64_t n_coarse, const int3
  * one persistent CTA per SM, dedicated epilogue warps, a double-buffered TMEM accumulator, split-K reduced inside the
  * kernel and grid barriers between dependent layers.  Same arithmetic and the same argument meaning as osb_conv_fwd_tc.
  *
- * A layer is described by an opaque record of osb_conv_desc_bytes() bytes, filled on the HOST by osb_conv_desc_fill and
- * copied by the caller into device memory (descs_dev) before osb_conv_chain_launch; the launch also reads the host copy.
+ * A layer is described by an opaque record of osb_conv_desc_bytes() bytes, filled on the HOST by osb_conv_desc_fill; the
+ * launch passes the records to the kernel as launch parameters (16 layers per launch, longer lists in several launches).
  *   wtiles          osb_conv_pack_weight_tiles(w [K,cin,cout]) -- tile-major, pre-swizzled B operands
  *   cmap/cmap_cout  non-NULL: dense transposed stride-2 convolution as in osb_convtr_fwd_tc (wtiles of the [1,cin,kvol*cout]
  *                   matrix, cout = kvol*cmap_cout, cmap = the stride-2 map [kvol, n_out] of the matching strided conv)
@@ -208,8 +208,7 @@ int osb_conv_desc_fill(void *desc_host, const void *src0, int32_t c0, const void
                        int64_t n_out, int32_t K, const void *wtiles, int32_t cout, const float *scale, const float *shift,
                        const void *res, int32_t relu, void *out_split, float *out_f32, const int32_t *out_row_map,
                        const int32_t *cmap, int32_t cmap_cout, void *ws, size_t ws_bytes, int32_t barrier_before);
-int osb_conv_chain_launch(const void *descs_dev, const void *descs_host, int32_t n_layers, void *grid_barrier,
-                          int32_t flags, void *stream);
+int osb_conv_chain_launch(const void *descs_host, int32_t n_layers, void *grid_barrier, int32_t flags, void *stream);
 
 /* Process-wide tuning knobs (tile shapes, ring depths, split factors, profiling hooks).  They select between
  * equivalent schedules and never change results; unknown names fail.  Names: see csrc/conv_chain.cu, csrc/conv_tc.cu. */

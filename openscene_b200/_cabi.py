@@ -43,7 +43,7 @@ SIGNATURES = {
     'osb_conv_chain_grid': (c_int, []),
     'osb_conv_chain_workspace_bytes': (SZ, [I64, I32, I32, I32]),
     'osb_conv_desc_fill': (c_int, [P, P, I32, P, I32, P, I64, I32, P, I32, P, P, P, I32, P, P, P, P, I32, P, SZ, I32]),
-    'osb_conv_chain_launch': (c_int, [P, P, I32, P, I32, P]),
+    'osb_conv_chain_launch': (c_int, [P, I32, P, I32, P]),
     'osb_tuning_set': (c_int, [c_char_p, I64]),
     'osb_conv_stem_fused': (c_int, [P, I32, P, I64, P, I64, I32, I32, P, I32, P, P, I32, P, P, P]),
     'osb_f32_to_split': (c_int, [P, I64, I32, P, P]),

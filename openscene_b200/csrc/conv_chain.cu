@@ -33,21 +33,23 @@
 
 namespace osb {
 
-constexpr int CH_THREADS = 512;
+constexpr int CH_THREADS = 384;                  // 12 warps (3 per scheduler -> 168 registers each): 4 epilogue, 1 weights, 2 MMA issuers, 5 gather
 constexpr int CH_M = 128;                        // rows per sub-tile (UMMA M)
 constexpr int CH_A_BYTES = CH_M * 128;           // one row slot: 128 rows x one 32-channel block
 constexpr int CH_STG_BYTES = 4 * 4096;           // epilogue staging: 4 warps x (32 rows x 128 B)
 constexpr int CH_SS_FLOATS = 768;                // folded BN constants kept in shared memory per layer (scale | shift)
 constexpr int CH_MAX_SA = 12, CH_MAX_SB = 4;
-// Warp roles (16 warps).  Measured with per-role cycle counters (profiles/r02_chain_roles.md): the gather producers are
-// instruction-issue bound (~1000 cycles of their own work per 16 KB row slot with 4 warps), the epilogue idles 95 % of the time.
+// Warp roles.  Measured with per-role cycle counters (profiles/r02_chain_roles.md): every role is ONE warp walking a
+// dependent instruction chain, so its fixed cost per row slot (barrier wait, address set-up, arrival: 300-500 cycles) is
+// latency, not throughput.  Gather producers therefore own whole slots (warp w fills every CH_A_WARPS-th slot, 32 copy
+// instructions behind one wait / one arrival), the epilogue (idle 90 % of the time) gets four warps for both TMEM buffers.
 constexpr int CH_W_EPI = 0;                       // warps 0-3: epilogue (warp % 4 = TMEM lane quarter), both accumulator buffers
 constexpr int CH_W_B = 4;                         // weight tiles
 constexpr int CH_W_MMA = 5;                       // warps 5, 6: MMA issuers; warp 5 owns the TMEM allocation
-constexpr int CH_W_A = 8;                         // warps 8-15: gathered rows, 16 rows of every slot each
-constexpr int CH_A_WARPS = 8;
-constexpr int CH_PEND = 3;                       // row slots a producer thread keeps in flight before it announces the oldest
+constexpr int CH_W_A = 7;                         // warps 7-11: gathered rows, one whole 128-row slot at a time each
+constexpr int CH_A_WARPS = 5;
 constexpr int CH_DESC_WORDS = 48;                // sizeof(ConvDesc) / 4
+constexpr int CH_MAX_LAYERS = 16;                // layers per launch: the descriptors travel as kernel parameters (3 KB)
 
 struct __align__(16) ConvDesc {
   const uint8_t *src0, *src1;      // split rows of the (up to) two sources ([src0 | src1] = ME.cat)
@@ -70,6 +72,10 @@ struct __align__(16) ConvDesc {
   int pad[8];
 };
 static_assert(sizeof(ConvDesc) == CH_DESC_WORDS * 4, "ConvDesc layout");
+// The layer list lives in the kernel's parameter (constant) space: every field is a warp-uniform value to the compiler, so
+// the single-thread roles (MMA issuers, weight producer) keep their slot / descriptor arithmetic on the uniform datapath
+// instead of paying vector->uniform register moves in front of every tcgen05.mma (profiles/r02_chain_roles.md).
+struct ChainArgs { ConvDesc d[CH_MAX_LAYERS]; };
 
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -130,6 +136,9 @@ __device__ __forceinline__ void grid_barrier(unsigned *gbar, unsigned &gen) {
 #define CH_PROF_BEGIN() const long long _t0 = prof ? clock64() : 0
 #define CH_PROF_END(var) do { if (prof) var += clock64() - _t0; } while (0)
 
+// keep a value in its register: stops the compiler from re-deriving shared-window addresses (S2R + shifts) in hot loops
+#define CH_KEEP(x) asm volatile("" : "+r"(x))
+
 // 16-byte global -> shared copy; `ignore` != 0 writes zeros instead (a missing neighbour row)
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void *src, uint32_t ignore) {
   asm volatile(
@@ -142,7 +151,7 @@ __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void *src, 
 
 // ------------------------------------------------------------------------------------ the kernel
 __global__ void __launch_bounds__(CH_THREADS, 1)
-k_conv_chain(const ConvDesc *__restrict__ descs, int n_layers, unsigned *gbar, int sa, int sb, int bslot, int flags,
+k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gbar, int sa, int sb, int bslot, int flags,
              long long *dbg_clock) {
   extern __shared__ uint8_t smem_raw[];
   // All hot-loop addressing is done on 32-bit shared-window addresses computed once; the few generic accesses (descriptor,
@@ -153,24 +162,24 @@ k_conv_chain(const ConvDesc *__restrict__ descs, int n_layers, unsigned *gbar, i
   const uint32_t a_ring = base_u32;                                          // row slots
   const uint32_t b_ring = a_ring + (uint32_t)sa * CH_A_BYTES;                // weight slots (bslot is a multiple of 1024)
   const uint32_t stg_u32 = b_ring + (uint32_t)sb * (uint32_t)bslot;          // epilogue staging: 4 warps x 4 KB
+  uint32_t a_ring_k = a_ring, b_ring_k = b_ring;
+  CH_KEEP(a_ring_k); CH_KEEP(b_ring_k);
   uint8_t *aux = smem + (stg_u32 - base_u32) + CH_STG_BYTES;
   float *s_ss = reinterpret_cast<float *>(aux);                              // [scale x CH_SS_FLOATS | shift x CH_SS_FLOATS]
-  ConvDesc *s_desc = reinterpret_cast<ConvDesc *>(s_ss + 2 * CH_SS_FLOATS);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(s_desc) + 256);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(s_ss + 2 * CH_SS_FLOATS);
   uint32_t *s_misc = reinterpret_cast<uint32_t *>(bars + 40);                // [0] TMEM base
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (flags & 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const bool prof = dbg_clock != nullptr;
-  const bool legacy_done = !(flags & 0x10000);     // default: self-tracking noinc arrivals + proxy fence on the consumer side
   long long pw0 = 0, pw1 = 0, pw2 = 0, pt = 0;     // cycles in this role's waits (up to three kinds) and in its loop
   if (dbg_clock && tid == 0) dbg_clock[blockIdx.x * 32 + 0] = clock64();
-  const uint32_t fullA = smem_u32(bars), emptyA = smem_u32(bars + 12);
-  const uint32_t fullB = smem_u32(bars + 24), emptyB = smem_u32(bars + 28);
-  const uint32_t accFull = smem_u32(bars + 32), accEmpty = smem_u32(bars + 34);
+  uint32_t fullA = smem_u32(bars), emptyA = fullA + 12 * 8, fullB = fullA + 24 * 8, emptyB = fullA + 28 * 8;
+  uint32_t accFull = fullA + 32 * 8, accEmpty = fullA + 34 * 8;
+  CH_KEEP(fullA); CH_KEEP(emptyA); CH_KEEP(fullB); CH_KEEP(emptyB); CH_KEEP(accFull); CH_KEEP(accEmpty);
 
   if (tid == 0) {
-    for (int s = 0; s < sa; ++s) { mbar_init(fullA + 8 * s, legacy_done ? CH_A_WARPS * 32 : CH_A_WARPS); mbar_init(emptyA + 8 * s, 1); }
+    for (int s = 0; s < sa; ++s) { mbar_init(fullA + 8 * s, 32); mbar_init(emptyA + 8 * s, 1); }   // fullA: the 32 lanes of the slot's warp
     for (int s = 0; s < sb; ++s) { mbar_init(fullB + 8 * s, 1); mbar_init(emptyB + 8 * s, 2); }   // emptyB: one arrival per issuer
     for (int b = 0; b < 2; ++b) { mbar_init(accFull + 8 * b, 2); mbar_init(accEmpty + 8 * b, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -191,13 +200,11 @@ k_conv_chain(const ConvDesc *__restrict__ descs, int n_layers, unsigned *gbar, i
 
   // pipeline state of this thread's role; persists over items and layers
   uint32_t a_slot = 0, a_phase = 0, b_slot = 0, b_phase = 0, n_item = 0;
-  uint32_t arr_slot = 0, n_pend = 0;               // A producers (producer-side completion): oldest slot not yet announced
+  uint32_t g_slot = 0;                             // gather producers: row slots the CTA has gone through (slot g belongs to warp g % CH_A_WARPS)
 
   for (int L = 0; L < n_layers; ++L) {
-    __syncthreads();                                   // every role is done with the previous layer (and with s_desc)
-    if (tid < CH_DESC_WORDS) reinterpret_cast<uint32_t *>(s_desc)[tid] = __ldg(reinterpret_cast<const uint32_t *>(descs + L) + tid);
-    __syncthreads();
-    // the layer's scalars, once per layer into registers (the role loops below must not chase them through shared memory)
+    __syncthreads();                                   // every role is done with the previous layer (and with s_ss)
+    const ConvDesc *s_desc = &args.d[L];               // parameter space: uniform loads
     const int d_K = s_desc->K, d_nb0 = s_desc->nb0, d_nb1 = s_desc->nb1, d_nt = s_desc->nt, d_n_ntiles = s_desc->n_ntiles;
     const int d_m_tiles = s_desc->m_tiles, d_nsplit = s_desc->nsplit, d_nsub_max = s_desc->nsub_max, d_sps = s_desc->stages_per_split;
     const int64_t d_n_out = s_desc->n_out;
@@ -244,7 +251,7 @@ k_conv_chain(const ConvDesc *__restrict__ descs, int n_layers, unsigned *gbar, i
               mbar_expect_tx(fb, 0u);
             } else {
               mbar_expect_tx(fb, b_bytes);
-              bulk_g2s(b_ring + b_slot * (uint32_t)bslot, wtiles + ((int64_t)t * d_n_ntiles + nti) * b_bytes, b_bytes, fb);
+              bulk_g2s(b_ring_k + b_slot * (uint32_t)bslot, wtiles + ((int64_t)t * d_n_ntiles + nti) * b_bytes, b_bytes, fb);
             }
           }
           __syncwarp();
@@ -268,38 +275,70 @@ k_conv_chain(const ConvDesc *__restrict__ descs, int n_layers, unsigned *gbar, i
         { CH_PROF_BEGIN(); mbar_wait(accEmpty + 8 * buf, ((n_item >> 1) & 1u) ^ 1u); CH_PROF_END(pw2); }   // the epilogue drained this buffer
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t dcol = tmem_base + buf * 256u + (uint32_t)mi * 128u;
-        for (int t = t_begin; t < t_end; ++t) {
-          if (mine) {
-            uint32_t sl = a_slot + (uint32_t)mi, ph = a_phase;             // my row slot of this stage
-            if (sl >= (uint32_t)sa) { sl -= (uint32_t)sa; ph ^= 1u; }
-            { CH_PROF_BEGIN(); mbar_wait(fullB + 8 * b_slot, b_phase); CH_PROF_END(pw0); }
-            { CH_PROF_BEGIN(); mbar_wait(fullA + 8 * sl, ph); CH_PROF_END(pw1); }
-            if (legacy_done) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) writes -> UMMA reads
-            if (!(flags & 0x2000)) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (flags & 0x4000) {                     // tuning: plain arrivals instead of tcgen05.commit (only without MMAs)
-              if (lane == 0) { mbar_arrive(emptyA + 8 * sl); mbar_arrive(emptyB + 8 * b_slot); }
-            } else if (elect_one()) {
-              const uint64_t db = umma_desc(b_ring + b_slot * (uint32_t)bslot);
-              const uint64_t da = umma_desc(a_ring + sl * (uint32_t)CH_A_BYTES);
-              // 128-byte line = [hi ch0-15 | hi ch16-31 | lo ch0-15 | lo ch16-31]; +2 per 32-byte K slice
+        // two stages per iteration: the fixed cost of an iteration (waits, proxy fence, election, descriptor set-up) is a
+        // dependent chain of a few hundred cycles; 12 MMAs behind it instead of 6
+        for (int t = t_begin; t < t_end;) {
+          const int nst = min(2, t_end - t);
+          uint32_t sl[2], sph[2], bs[2], bph[2];
+          {
+            uint32_t as_ = a_slot + (uint32_t)mi, ap_ = a_phase, bs_ = b_slot, bp_ = b_phase;
+            if (as_ >= (uint32_t)sa) { as_ -= (uint32_t)sa; ap_ ^= 1u; }
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                if (flags & 0x400) break;             // tuning: no MMAs
-                umma_bf16(dcol, da + 2 * h, db + 2 * h, idesc, (h == 0 && t == t_begin) ? 0u : 1u);   // hi * Whi
-                umma_bf16(dcol, da + 2 * h, db + 2 * h + 4, idesc, 1u);                                // hi * Wlo
-                umma_bf16(dcol, da + 2 * h + 4, db + 2 * h, idesc, 1u);                                // lo * Whi
+            for (int jx = 0; jx < 2; ++jx) {
+              sl[jx] = as_; sph[jx] = ap_; bs[jx] = bs_; bph[jx] = bp_;
+              as_ += (uint32_t)nsub; if (as_ >= (uint32_t)sa) { as_ -= (uint32_t)sa; ap_ ^= 1u; }
+              if (++bs_ == (uint32_t)sb) { bs_ = 0; bp_ ^= 1u; }
+            }
+          }
+          if (mine) {
+            { CH_PROF_BEGIN(); mbar_wait(fullB + 8 * bs[0], bph[0]); if (nst == 2) mbar_wait(fullB + 8 * bs[1], bph[1]); CH_PROF_END(pw0); }
+            { CH_PROF_BEGIN(); mbar_wait(fullA + 8 * sl[0], sph[0]); if (nst == 2) mbar_wait(fullA + 8 * sl[1], sph[1]); CH_PROF_END(pw1); }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) writes -> UMMA reads
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (flags & 0x4000) {                     // tuning: plain arrivals instead of tcgen05.commit (only without MMAs)
+              if (lane == 0) {
+#pragma unroll
+                for (int jx = 0; jx < 2; ++jx)
+                  if (jx < nst) { mbar_arrive(emptyA + 8 * sl[jx]); mbar_arrive(emptyB + 8 * bs[jx]); }
               }
-              umma_commit(emptyA + 8 * sl);                                 // row slot free when these MMAs retire
-              umma_commit(emptyB + 8 * b_slot);                             // weight slot: one arrival per issuer
+            } else if (elect_one()) {
+#pragma unroll
+              for (int jx = 0; jx < 2; ++jx) {
+                if (jx < nst) {
+                  const uint64_t db = umma_desc(b_ring_k + bs[jx] * (uint32_t)bslot);
+                  const uint64_t da = umma_desc(a_ring_k + sl[jx] * (uint32_t)CH_A_BYTES);
+                  // 128-byte line = [hi ch0-15 | hi ch16-31 | lo ch0-15 | lo ch16-31]; +2 per 32-byte K slice
+#pragma unroll
+                  for (int h = 0; h < 2; ++h) {
+                    if (flags & 0x400) break;         // tuning: no MMAs
+                    umma_bf16(dcol, da + 2 * h, db + 2 * h, idesc, (h == 0 && jx == 0 && t == t_begin) ? 0u : 1u);   // hi * Whi
+                    umma_bf16(dcol, da + 2 * h, db + 2 * h + 4, idesc, 1u);                                          // hi * Wlo
+                    umma_bf16(dcol, da + 2 * h + 4, db + 2 * h, idesc, 1u);                                          // lo * Whi
+                  }
+                  umma_commit(emptyA + 8 * sl[jx]);                         // row slot free when these MMAs retire
+                  umma_commit(emptyB + 8 * bs[jx]);                         // weight slot: one arrival per issuer
+                }
+              }
             }
           } else {
-            mbar_wait(fullB + 8 * b_slot, b_phase);                         // stay in step with the slot's phase ...
-            if (lane == 0) mbar_arrive(emptyB + 8 * b_slot);                // ... nothing of mine reads this weight tile
+#pragma unroll
+            for (int jx = 0; jx < 2; ++jx) {
+              if (jx < nst) {
+                mbar_wait(fullB + 8 * bs[jx], bph[jx]);                     // stay in step with the slot's phase ...
+                if (lane == 0) mbar_arrive(emptyB + 8 * bs[jx]);            // ... nothing of mine reads this weight tile
+              }
+            }
           }
           __syncwarp();
-          a_slot += (uint32_t)nsub;
-          if (a_slot >= (uint32_t)sa) { a_slot -= (uint32_t)sa; a_phase ^= 1u; }
-          if (++b_slot == (uint32_t)sb) { b_slot = 0; b_phase ^= 1; }
+#pragma unroll
+          for (int jx = 0; jx < 2; ++jx) {
+            if (jx < nst) {
+              a_slot += (uint32_t)nsub;
+              if (a_slot >= (uint32_t)sa) { a_slot -= (uint32_t)sa; a_phase ^= 1u; }
+              if (++b_slot == (uint32_t)sb) { b_slot = 0; b_phase ^= 1; }
+            }
+          }
+          t += nst;
         }
         if (mine) { if (elect_one()) umma_commit(accFull + 8 * buf); }
         else if (lane == 0) mbar_arrive(accFull + 8 * buf);
@@ -307,95 +346,73 @@ k_conv_chain(const ConvDesc *__restrict__ descs, int n_layers, unsigned *gbar, i
         ++n_item;
       }
     } else if (warp >= CH_W_A) {
-      // ================= gathered A rows: 16 rows of each slot per warp (8 warps) ====================
-      // 8 lanes cover one 128-byte row line (one L2 line), 4 rows per warp instruction, 4 instructions per slot;
-      // the destination carries the 128B swizzle (chunk ^ (row & 7)); a missing neighbour is a zero-fill copy.
-      // The loop is instruction-issue bound (profiles/r02_chain_roles.md): everything that does not change per copy is
-      // hoisted, addresses are 32-bit shared-window offsets, and 8 warps share the 128 rows of a slot.
+      // ================= gathered A rows: warp w fills every CH_A_WARPS-th row slot, all 128 rows of it ====================
+      // 8 lanes cover one 128-byte row line (one L2 line), 4 rows per copy instruction, 32 instructions per slot behind ONE
+      // barrier wait and ONE (self-tracking) arrival; the destination carries the 128B swizzle (chunk ^ (row & 7)); a
+      // missing neighbour is a zero-fill copy.  The slot's 128 row indices are four coalesced loads (lane l: rows l, l+32, ..)
+      // fetched one slot of this warp ahead and handed round by shuffles.
       const int w = warp - CH_W_A, j = lane & 7, q = lane >> 3;
       const int32_t *nbr = s_desc->nbr;
       const uint8_t *src0 = s_desc->src0 + j * 16, *src1 = s_desc->src1 + j * 16;
       const uint32_t rb0 = (uint32_t)d_nb0 * 128u, rb1 = (uint32_t)d_nb1 * 128u;
-      // this thread's 4 destinations inside a slot: row 16w + 4i + q, chunk j ^ (row & 7)
-      uint32_t dst_off[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int row = w * 16 + 4 * i + q;
-        dst_off[i] = (uint32_t)row * 128u + (uint32_t)((j ^ (row & 7)) << 4);
-      }
+      const uint32_t off_even = (uint32_t)q * 128u + (uint32_t)((j ^ q) << 4);                 // rows 8n + q
+      const uint32_t off_odd = (uint32_t)(4 + q) * 128u + (uint32_t)((j ^ (4 + q)) << 4);      // rows 8n + 4 + q
       CH_FOR_ITEMS() {
         (void)nti;
-        const int64_t row0 = (int64_t)m * CH_M + w * 16 + q;
-        int32_t cur[2][4], nxt[2][4];
-        auto fetch = [&](int k, int32_t (&r)[2][4]) {
-          const int32_t *nk = nbr ? nbr + (int64_t)k * d_n_out : nullptr;
+        const int n_slots = (t_end - t_begin) * nsub;
+        // my slots of this item: local indices jl with (g_slot + jl) % CH_A_WARPS == w, where g_slot counts the CTA's slots
+        int jl = (int)((uint32_t)(w + CH_A_WARPS - (int)(g_slot % CH_A_WARPS)) % CH_A_WARPS);
+        auto decode = [&](int jl_, int &k_, int &cb_, int &s_) {
+          const int tt = t_begin + (nsub == 2 ? (jl_ >> 1) : jl_);
+          s_ = nsub == 2 ? (jl_ & 1) : 0;
+          k_ = tt / nb; cb_ = tt - k_ * nb;
+        };
+        auto fetch = [&](int k_, int s_, int32_t (&r)[4]) {
+          const int32_t *nk = nbr ? nbr + (int64_t)k_ * d_n_out : nullptr;
 #pragma unroll
-          for (int s = 0; s < 2; ++s) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int64_t o = row0 + s * CH_M + 4 * i;
-              r[s][i] = (s < nsub && o < d_n_out) ? (nk ? __ldg(nk + o) : (int32_t)o) : -1;
-            }
+          for (int i = 0; i < 4; ++i) {
+            const int64_t o = (int64_t)(m + s_) * CH_M + 32 * i + lane;
+            r[i] = (o < d_n_out) ? (nk ? __ldg(nk + o) : (int32_t)o) : -1;
           }
         };
-        int k_cur = t_begin / nb;
-        if (t_begin < t_end) fetch(k_cur, nxt);
-        for (int t = t_begin; t < t_end;) {
+        int32_t nxt[4];
+        int k_n = 0, cb_n = 0, s_n = 0;
+        if (jl < n_slots) { decode(jl, k_n, cb_n, s_n); fetch(k_n, s_n, nxt); }
+        for (; jl < n_slots; jl += CH_A_WARPS) {
+          int32_t cur[4];
           {
             CH_PROF_BEGIN();
 #pragma unroll
-            for (int s = 0; s < 2; ++s)
-#pragma unroll
-              for (int i = 0; i < 4; ++i) cur[s][i] = nxt[s][i];
-            if (prof) { int acc_ = 0; for (int s = 0; s < 2; ++s) for (int i = 0; i < 4; ++i) acc_ += cur[s][i]; if (acc_ == 0x7fffffff) pw2 += 1; }   // force the loads to land here
+            for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+            if (prof) { if (cur[0] + cur[1] + cur[2] + cur[3] == 0x7fffffff) pw2 += 1; }   // force the loads to land here
             CH_PROF_END(pw1);
           }
-          const int t_next_k = min((k_cur + 1) * nb, t_end);                // first stage of the next offset
-          if (t_next_k < t_end) fetch(k_cur + 1, nxt);                      // one offset ahead: latency behind this offset's copies
-          for (; t < t_next_k; ++t) {
-            const int cb = t - k_cur * nb;
-            const bool first = cb < d_nb0;
-            const uint8_t *src = (first ? src0 : src1) + (first ? cb : cb - d_nb0) * 128;
-            const uint32_t rb = first ? rb0 : rb1;
-            for (int s = 0; s < nsub; ++s) {
-              { CH_PROF_BEGIN(); mbar_wait(emptyA + 8 * a_slot, a_phase ^ 1); CH_PROF_END(pw0); }
-              const uint32_t a_dst = a_ring + a_slot * (uint32_t)CH_A_BYTES;
-              if (!(flags & 0x100)) {                 // tuning: bit 8 = no row copies
+          const int cb = cb_n;
+          if (jl + CH_A_WARPS < n_slots) { decode(jl + CH_A_WARPS, k_n, cb_n, s_n); fetch(k_n, s_n, nxt); }   // my next slot's indices
+          // ring slot / phase of local slot jl
+          const uint32_t lin = a_slot + (uint32_t)jl, wraps = lin / (uint32_t)sa;
+          const uint32_t sl = lin - wraps * (uint32_t)sa, ph = a_phase ^ (wraps & 1u);
+          const bool first = cb < d_nb0;
+          const uint8_t *src = (first ? src0 : src1) + (first ? cb : cb - d_nb0) * 128;
+          const uint32_t rb = first ? rb0 : rb1;
+          { CH_PROF_BEGIN(); mbar_wait(emptyA + 8 * sl, ph ^ 1); CH_PROF_END(pw0); }
+          const uint32_t a_dst = a_ring_k + sl * (uint32_t)CH_A_BYTES;
+          if (!(flags & 0x100)) {                     // tuning: bit 8 = no row copies
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const int32_t r = (s == 0) ? cur[0][i] : cur[1][i];
-                  const uint32_t rr = r < 0 ? 0u : (uint32_t)r;
-                  cp_async16_zfill(a_dst + dst_off[i], src + (uint64_t)rr * rb, r < 0 ? 1u : 0u);
-                }
-              }
-              if (legacy_done) {                      // 32 self-tracking arrivals per warp, fired by the copy engine
-                cp_async_arrive_noinc(fullA + 8 * a_slot);
-              } else {
-                // Completion on the PRODUCER side, CH_PEND slots behind the issue front: wait for this thread's copies of
-                // the oldest pending slot, make them visible to the async proxy, one arrival per warp.
-                asm volatile("cp.async.commit_group;" ::: "memory");
-                if (++n_pend > CH_PEND) {
-                  asm volatile("cp.async.wait_group %0;" ::"n"(CH_PEND) : "memory");
-                  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                  __syncwarp();
-                  if (lane == 0) mbar_arrive(fullA + 8 * arr_slot);
-                  if (++arr_slot == (uint32_t)sa) arr_slot = 0;
-                  --n_pend;
-                }
-              }
-              if (++a_slot == (uint32_t)sa) { a_slot = 0; a_phase ^= 1; }
+            for (int i = 0; i < 32; ++i) {            // rows 4i + q
+              const int32_t r = __shfl_sync(0xffffffffu, cur[i >> 3], (4 * i + q) & 31);
+              const uint32_t rr = r < 0 ? 0u : (uint32_t)r;
+              cp_async16_zfill(a_dst + (uint32_t)(i >> 1) * 1024u + ((i & 1) ? off_odd : off_even), src + (uint64_t)rr * rb, r < 0 ? 1u : 0u);
             }
           }
-          ++k_cur;
+          cp_async_arrive_noinc(fullA + 8 * sl);      // 32 self-tracking arrivals, fired by the copy engine
         }
-      }
-      if (!legacy_done) {                             // drain: the last slots of the layer
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        for (; n_pend > 0; --n_pend) {
-          if (lane == 0) mbar_arrive(fullA + 8 * arr_slot);
-          if (++arr_slot == (uint32_t)sa) arr_slot = 0;
+        // every producer warp advances the shared view of the ring by the whole item
+        g_slot += (uint32_t)n_slots;
+        {
+          const uint32_t lin = a_slot + (uint32_t)n_slots, wraps = lin / (uint32_t)sa;
+          a_slot = lin - wraps * (uint32_t)sa;
+          a_phase ^= (wraps & 1u);
         }
       }
     } else if (warp < 4) {
@@ -536,7 +553,7 @@ k_conv_chain(const ConvDesc *__restrict__ descs, int n_layers, unsigned *gbar, i
     if (d_nsplit > 1) {
       // ---- split-K: every partial is in global memory after this barrier; reduce + epilogue by all threads of the grid
       grid_barrier(gbar, bar_gen);
-      const ConvDesc &d = *s_desc;
+      const ConvDesc &d = args.d[L];
       const int groups = d.cout / 8;
       const int64_t total = d.n_out * groups;
       for (int64_t e = (int64_t)blockIdx.x * CH_THREADS + tid; e < total; e += (int64_t)gridDim.x * CH_THREADS) {
@@ -723,41 +740,50 @@ int osb_conv_desc_fill(void *desc_host, const void *src0, int32_t c0, const void
   return 0;
 }
 
-int osb_conv_chain_launch(const void *descs_dev, const void *descs_host, int32_t n_layers, void *grid_barrier_dev, int32_t flags,
-                          void *stream_) {
+int osb_conv_chain_launch(const void *descs_host, int32_t n_layers, void *grid_barrier_dev, int32_t flags, void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  OSB_CHECK(descs_dev && descs_host && n_layers >= 1, "osb_conv_chain_launch: bad arguments");
+  OSB_CHECK(descs_host && n_layers >= 1, "osb_conv_chain_launch: bad arguments");
   const ConvDesc *h = (const ConvDesc *)descs_host;
-  int nt_max = 0, need_bar = 0;
   for (int i = 0; i < n_layers; ++i) {
-    nt_max = std::max(nt_max, h[i].nt);
-    need_bar |= (h[i].barrier_before || h[i].nsplit > 1);
     OSB_CHECK(i > 0 || !h[i].barrier_before, "osb_conv_chain_launch: the first layer of a launch cannot ask for a barrier");
     // a split layer's reduce phase is not followed by a barrier: the next layer may only reuse the partial buffer behind one
     OSB_CHECK(i == 0 || h[i].barrier_before || h[i].nsplit == 1 || h[i - 1].nsplit == 1 || h[i].partial != h[i - 1].partial,
               "osb_conv_chain_launch: layers %d and %d share a split workspace without a barrier between them", i - 1, i);
   }
-  OSB_CHECK(!need_bar || grid_barrier_dev != nullptr, "osb_conv_chain_launch: this chain needs the grid-barrier words");
-  const int bslot = nt_max * 128;
-  const int fixed = 1024 + CH_STG_BYTES + 2 * CH_SS_FLOATS * 4 + 256 + 40 * 8 + 64;   // alignment slack, staging, BN constants, descriptor, barriers
-  int sb = g_chain_sb > 0 ? g_chain_sb : (bslot >= 32768 ? 2 : 3);
-  sb = std::min(sb, CH_MAX_SB);
-  int sa = (227 * 1024 - fixed - sb * bslot) / CH_A_BYTES;
-  if (g_chain_sa > 0) sa = std::min(sa, g_chain_sa);
-  sa = std::min(sa, CH_MAX_SA);
-  OSB_CHECK(sa >= CH_PEND + 2, "osb_conv_chain_launch: shared memory does not hold %d row slots", CH_PEND + 2);
-  const size_t smem_bytes = (size_t)sa * CH_A_BYTES + (size_t)sb * bslot + fixed;
   OSB_SMEM_ATTR_ONCE(k_conv_chain, 227 * 1024);
   const int grid = osb_conv_chain_grid();
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(CH_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
-  cfg.attrs = attr; cfg.numAttrs = (flags & 1) ? 1 : 0;
-  OSB_CUDA(cudaLaunchKernelEx(&cfg, k_conv_chain, (const ConvDesc *)descs_dev, (int)n_layers, (unsigned *)grid_barrier_dev, sa, sb,
-                              bslot, (int)((flags & 1) | (g_chain_dbg_skip << 8)), g_chain_dbg_clock));
-  OSB_LAUNCH_CHECK();
+  // the layer descriptors travel as kernel parameters: at most CH_MAX_LAYERS per launch, longer lists in several launches
+  // (a launch boundary orders everything, so the first layer of a later launch needs no grid barrier)
+  for (int l0 = 0; l0 < n_layers; l0 += CH_MAX_LAYERS) {
+    const int cnt = std::min(CH_MAX_LAYERS, n_layers - l0);
+    ChainArgs args;
+    memcpy(args.d, h + l0, sizeof(ConvDesc) * cnt);
+    args.d[0].barrier_before = 0;
+    int nt_max = 0, need_bar = 0;
+    for (int i = 0; i < cnt; ++i) {
+      nt_max = std::max(nt_max, args.d[i].nt);
+      need_bar |= (args.d[i].barrier_before || args.d[i].nsplit > 1);
+    }
+    OSB_CHECK(!need_bar || grid_barrier_dev != nullptr, "osb_conv_chain_launch: this chain needs the grid-barrier words");
+    const int bslot = nt_max * 128;
+    const int fixed = 1024 + CH_STG_BYTES + 2 * CH_SS_FLOATS * 4 + 40 * 8 + 64;   // alignment slack, staging, BN constants, barriers
+    int sb = g_chain_sb > 0 ? g_chain_sb : (bslot >= 32768 ? 2 : 3);
+    sb = std::min(sb, CH_MAX_SB);
+    int sa = (227 * 1024 - fixed - sb * bslot) / CH_A_BYTES;
+    if (g_chain_sa > 0) sa = std::min(sa, g_chain_sa);
+    sa = std::min(sa, CH_MAX_SA);
+    OSB_CHECK(sa >= 4, "osb_conv_chain_launch: shared memory does not hold four row slots");
+    const size_t smem_bytes = (size_t)sa * CH_A_BYTES + (size_t)sb * bslot + fixed;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(CH_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
+    cfg.attrs = attr; cfg.numAttrs = (flags & 1) ? 1 : 0;
+    OSB_CUDA(cudaLaunchKernelEx(&cfg, k_conv_chain, args, (int)cnt, (unsigned *)grid_barrier_dev, sa, sb, bslot,
+                                (int)((flags & 1) | (g_chain_dbg_skip << 8)), g_chain_dbg_clock));
+    OSB_LAUNCH_CHECK();
+  }
   return 0;
 }
 

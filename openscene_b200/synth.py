@@ -82,6 +82,16 @@ def scene(name, voxel=None, seed=0, batch_index=0):
     return voxel_coords(room_points(size, nf, voxel or 0.02, seed), voxel or 0.02, batch_index)
 
 
+def scene_points(name, seed=0):
+    """Raw float64 points [N_pts,3] (metres) and the voxel size of a named scene -- what ``Voxelizer.voxelize`` receives."""
+    if name == 'config5_lidar':
+        return lidar_points(790_000, seed), 0.05
+    if name.startswith('lidar_'):
+        return lidar_points(int(name.split('_')[1]), seed), 0.05
+    size, nf = ROOMS[name]
+    return room_points(size, nf, 0.02, seed), 0.02
+
+
 def text_embeddings(k, c=768, seed=0):
     rng = np.random.RandomState(1000 + seed)
     t = rng.normal(size=(k, c))

@@ -111,20 +111,17 @@ def pack_weight_tiles(w3, transpose_w=False):
 class ConvChain:
     """A list of convolution layers executed by osb_conv_chain_launch (one persistent launch per group of layers).
 
-    Descriptors are filled into pinned host memory with raw device addresses (ints), copied to the device once per
-    forward, and launched group by group: ``begin()``, ``add(...)`` per layer, ``cut()`` between launches, ``run()``."""
+    Descriptors are filled into host memory with raw device addresses (ints) and handed to the kernel as launch
+    parameters, group by group: ``begin()``, ``add(...)`` per layer, ``cut()`` between launches, ``run()``."""
 
     def __init__(self, device, max_layers=160):
         self.device = torch.device(device)
         self.dbytes = C.lib().osb_conv_desc_bytes()
         self.max_layers = max_layers
-        # pageable on purpose: the H2D copy below is then staged by the driver before copy_ returns, so the next forward may
-        # refill this buffer while the GPU is still several steps behind
-        self.host = torch.zeros(max_layers * self.dbytes, dtype=torch.uint8)
+        self.host = torch.zeros(max_layers * self.dbytes, dtype=torch.uint8)          # copied into the launch parameters
         with torch.cuda.device(self.device):
-            self.dev = torch.empty(max_layers * self.dbytes, dtype=torch.uint8, device=self.device)
             self.gbar = torch.zeros(4, dtype=torch.int32, device=self.device)       # {count, generation}: zeroed once
-        self.host_a, self.dev_a, self.gbar_a = self.host.data_ptr(), self.dev.data_ptr(), self.gbar.data_ptr()
+        self.host_a, self.gbar_a = self.host.data_ptr(), self.gbar.data_ptr()
         self._fill = C.lib().osb_conv_desc_fill
         self.begin()
 
@@ -155,11 +152,9 @@ class ConvChain:
     def run(self, flags=0, stream=None):
         self.cut()
         stream = stream if stream is not None else torch.cuda.current_stream().cuda_stream
-        with torch.cuda.device(self.device):
-            self.dev[:self.n * self.dbytes].copy_(self.host[:self.n * self.dbytes], non_blocking=True)
         fn = C.lib().osb_conv_chain_launch
         for (g0, cnt) in self.groups:
-            rc = fn(self.dev_a + g0 * self.dbytes, self.host_a + g0 * self.dbytes, cnt, self.gbar_a, flags, stream)
+            rc = fn(self.host_a + g0 * self.dbytes, cnt, self.gbar_a, flags, stream)
             if rc:
                 C.check(rc, 'osb_conv_chain_launch')
 
