@@ -136,6 +136,20 @@ __device__ __forceinline__ void grid_barrier(unsigned *gbar, unsigned &gen) {
 #define CH_PROF_BEGIN() const long long _t0 = prof ? clock64() : 0
 #define CH_PROF_END(var) do { if (prof) var += clock64() - _t0; } while (0)
 
+// one non-blocking-ish probe of an mbarrier phase (true = complete).  Several probes issued back to back overlap their
+// ~190-cycle round trips; a chain of mbar_wait calls pays them one after the other.
+__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done;
+}
+
 // keep a value in its register: stops the compiler from re-deriving shared-window addresses (S2R + shifts) in hot loops
 #define CH_KEEP(x) asm volatile("" : "+r"(x))
 
@@ -291,8 +305,18 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
             }
           }
           if (mine) {
-            { CH_PROF_BEGIN(); mbar_wait(fullB + 8 * bs[0], bph[0]); if (nst == 2) mbar_wait(fullB + 8 * bs[1], bph[1]); CH_PROF_END(pw0); }
-            { CH_PROF_BEGIN(); mbar_wait(fullA + 8 * sl[0], sph[0]); if (nst == 2) mbar_wait(fullA + 8 * sl[1], sph[1]); CH_PROF_END(pw1); }
+            {                                         // all barriers of the batch probed together (overlapping round trips)
+              CH_PROF_BEGIN();
+              const bool two = nst == 2;
+              const uint32_t b1 = two ? bs[1] : bs[0], bp1 = two ? bph[1] : bph[0], a1 = two ? sl[1] : sl[0], ap1 = two ? sph[1] : sph[0];
+              for (uint32_t it = 0;; ++it) {
+                const uint32_t ok = mbar_try(fullB + 8 * bs[0], bph[0]) & mbar_try(fullA + 8 * sl[0], sph[0]) &
+                                    mbar_try(fullB + 8 * b1, bp1) & mbar_try(fullA + 8 * a1, ap1);
+                if (ok) break;
+                if (it > (1u << 26)) __trap();
+              }
+              CH_PROF_END(pw1);
+            }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) writes -> UMMA reads
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (flags & 0x4000) {                     // tuning: plain arrivals instead of tcgen05.commit (only without MMAs)
