@@ -189,13 +189,13 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
   long long pw0 = 0, pw1 = 0, pw2 = 0, pt = 0;     // cycles in this role's waits (up to three kinds) and in its loop
   if (dbg_clock && tid == 0) dbg_clock[blockIdx.x * 32 + 0] = clock64();
   uint32_t fullA = smem_u32(bars), emptyA = fullA + 12 * 8, fullB = fullA + 24 * 8, emptyB = fullA + 28 * 8;
-  uint32_t accFull = fullA + 32 * 8, accEmpty = fullA + 34 * 8;
-  CH_KEEP(fullA); CH_KEEP(emptyA); CH_KEEP(fullB); CH_KEEP(emptyB); CH_KEEP(accFull); CH_KEEP(accEmpty);
+  uint32_t accFull = fullA + 32 * 8, accEmpty = fullA + 34 * 8, turnBar = fullA + 36 * 8;
+  CH_KEEP(fullA); CH_KEEP(emptyA); CH_KEEP(fullB); CH_KEEP(emptyB); CH_KEEP(accFull); CH_KEEP(accEmpty); CH_KEEP(turnBar);
 
   if (tid == 0) {
     for (int s = 0; s < sa; ++s) { mbar_init(fullA + 8 * s, 32); mbar_init(emptyA + 8 * s, 1); }   // fullA: the 32 lanes of the slot's warp
     for (int s = 0; s < sb; ++s) { mbar_init(fullB + 8 * s, 1); mbar_init(emptyB + 8 * s, 2); }   // emptyB: one arrival per issuer
-    for (int b = 0; b < 2; ++b) { mbar_init(accFull + 8 * b, 2); mbar_init(accEmpty + 8 * b, 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(accFull + 8 * b, 2); mbar_init(accEmpty + 8 * b, 4); mbar_init(turnBar + 8 * b, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == CH_W_MMA) {   // all 512 TMEM columns: two accumulator buffers of 256 columns (one CTA per SM, no contention)
@@ -214,6 +214,7 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
 
   // pipeline state of this thread's role; persists over items and layers
   uint32_t a_slot = 0, a_phase = 0, b_slot = 0, b_phase = 0, n_item = 0;
+  uint32_t n_turn = 0;                             // MMA issuers: batches issued so far (token protocol below)
   uint32_t g_slot = 0;                             // gather producers: row slots the CTA has gone through (slot g belongs to warp g % CH_A_WARPS)
 
   for (int L = 0; L < n_layers; ++L) {
@@ -319,6 +320,11 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) writes -> UMMA reads
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // The issuers take turns on the tensor pipe: tcgen05.mma issue blocks while the pipe's queue is full, so two
+            // threads issuing at the same time each take twice as long and the pipe idles while both do their set-up.
+            // Issuer 0 goes first; each passes the turn on after the first stage of its batch (the rest of its MMAs cover
+            // the other's wake-up).  Accumulators are disjoint, each is fed by one thread in stage order.
+            if (!(flags & 0x8000)) { CH_PROF_BEGIN(); mbar_wait(turnBar + 8 * (uint32_t)mi, mi == 0 ? ((n_turn & 1u) ^ 1u) : (n_turn & 1u)); CH_PROF_END(pw0); }
             if (flags & 0x4000) {                     // tuning: plain arrivals instead of tcgen05.commit (only without MMAs)
               if (lane == 0) {
 #pragma unroll
@@ -341,9 +347,11 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
                   }
                   umma_commit(emptyA + 8 * sl[jx]);                         // row slot free when these MMAs retire
                   umma_commit(emptyB + 8 * bs[jx]);                         // weight slot: one arrival per issuer
+                  if (jx == 0 && !(flags & 0x8000)) mbar_arrive(turnBar + 8 * (uint32_t)(1 - mi));   // pass the turn on
                 }
               }
             }
+            if ((flags & 0x4000) && !(flags & 0x8000) && lane == 0) mbar_arrive(turnBar + 8 * (uint32_t)(1 - mi));
           } else {
 #pragma unroll
             for (int jx = 0; jx < 2; ++jx) {
@@ -352,8 +360,13 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
                 if (lane == 0) mbar_arrive(emptyB + 8 * bs[jx]);            // ... nothing of mine reads this weight tile
               }
             }
+            if (!(flags & 0x8000)) {                  // keep the turn protocol going (one wait, one hand-over per batch)
+              mbar_wait(turnBar + 8 * (uint32_t)mi, mi == 0 ? ((n_turn & 1u) ^ 1u) : (n_turn & 1u));
+              if (lane == 0) mbar_arrive(turnBar + 8 * (uint32_t)(1 - mi));
+            }
           }
           __syncwarp();
+          ++n_turn;
 #pragma unroll
           for (int jx = 0; jx < 2; ++jx) {
             if (jx < nst) {
@@ -698,7 +711,7 @@ static int g_chain_grid = 0;             // tuning: CTAs per launch (0 = one per
 static int g_chain_sa = 0, g_chain_sb = 0;   // tuning: ring depths (0 = as many row slots as fit / 3 or 2 weight slots)
 static long long *g_chain_dbg_clock = nullptr;
 static int g_chain_dbg_skip = 0;         // tuning: bit0 no row copies, bit1 no weight loads, bit2 no MMAs, bit3 no stores,
-                                         // bit5 no tcgen05 fence, bit6 plain arrivals for commits, bit8 legacy (consumer-side) completion
+                                         // bit5 no tcgen05 fence, bit6 plain arrivals for commits, bit7 no turn-taking between the issuers
 
 int osb_tuning_set(const char *name, int64_t value) {
   const std::string n(name ? name : "");

@@ -42,7 +42,7 @@ print(f'# {workload} n={n} {cin}->{cout} k={ks}')
 print(f'legacy k_conv_tc                         {timed(lambda: tc.conv_tc(x, cin, None, 0, nbr, n, ks ** 3, wp, cout)):8.1f} us')
 SETS = [
     ('chain default (noinc arrivals, consumer-side fence)', {}),
-    ('producer-side completion (0x100)', {'chain_dbg_skip': 0x100}),
+    ('no turn-taking between issuers (0x80)', {'chain_dbg_skip': 0x80}),
     ('nsub=1', {'chain_nsub': 1}),
     ('no A,B,MMA (0x7)', {'chain_dbg_skip': 0x7}),
     ('no A,B (0x3)', {'chain_dbg_skip': 0x3}),
