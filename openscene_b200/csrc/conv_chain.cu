@@ -10,8 +10,9 @@
 //   warps 0-3   epilogue of both TMEM accumulator buffers: TMEM -> registers -> BN affine / residual / ReLU -> swizzled
 //               staging tile -> full-line coalesced stores (split rows, fp32 rows, or raw split-K partials)
 //   warp 4      weight tiles: one cp.async.bulk per stage from the tile-major, pre-swizzled packing (no tensor map)
-//   warps 5-6   tcgen05.mma issuers (one thread each): warp 5 owns sub-tile 0 of an item, warp 6 sub-tile 1; warp 5 owns TMEM
-//   warps 8-15  gathered A rows: cp.async 16 B x 8 lanes per 128-byte row line, hand-applied 128B swizzle, the kernel
+//   warps 5-8   tcgen05.mma issuers (one thread each), one per sub-tile of an item (up to four 128-row sub-tiles share every
+//               weight tile); a single thread can issue one MMA per ~90 cycles, the pipe needs 48 for M128 x N96 x K16
+//   warps 9-15  gathered A rows: cp.async 16 B x 8 lanes per 128-byte row line, hand-applied 128B swizzle, the kernel
 //               map read per offset straight from global memory, one offset ahead
 //
 // What changed against conv_tc.cu, and why (profiles/r01_ncu_full_conv_tc_96x96_k3_final.md, DESIGN.md "slot model"):
@@ -33,7 +34,7 @@
 
 namespace osb {
 
-constexpr int CH_THREADS = 384;                  // 12 warps (3 per scheduler -> 168 registers each): 4 epilogue, 1 weights, 2 MMA issuers, 5 gather
+constexpr int CH_THREADS = 512;                  // 16 warps: 4 epilogue, 1 weights, 4 MMA issuers, 7 gather
 constexpr int CH_M = 128;                        // rows per sub-tile (UMMA M)
 constexpr int CH_A_BYTES = CH_M * 128;           // one row slot: 128 rows x one 32-channel block
 constexpr int CH_STG_BYTES = 4 * 4096;           // epilogue staging: 4 warps x (32 rows x 128 B)
@@ -43,11 +44,12 @@ constexpr int CH_MAX_SA = 12, CH_MAX_SB = 4;
 // dependent instruction chain, so its fixed cost per row slot (barrier wait, address set-up, arrival: 300-500 cycles) is
 // latency, not throughput.  Gather producers therefore own whole slots (warp w fills every CH_A_WARPS-th slot, 32 copy
 // instructions behind one wait / one arrival), the epilogue (idle 90 % of the time) gets four warps for both TMEM buffers.
-constexpr int CH_W_EPI = 0;                       // warps 0-3: epilogue (warp % 4 = TMEM lane quarter), both accumulator buffers
+constexpr int CH_W_EPI = 0;                       // warps 0-3: epilogue (warp % 4 = TMEM lane quarter) of every sub-tile in turn
 constexpr int CH_W_B = 4;                         // weight tiles
-constexpr int CH_W_MMA = 5;                       // warps 5, 6: MMA issuers; warp 5 owns the TMEM allocation
-constexpr int CH_W_A = 7;                         // warps 7-11: gathered rows, one whole 128-row slot at a time each
-constexpr int CH_A_WARPS = 5;
+constexpr int CH_W_MMA = 5;                       // warps 5-8: MMA issuers, one per sub-tile of an item; warp 5 owns the TMEM allocation
+constexpr int CH_MMA_WARPS = 4;
+constexpr int CH_W_A = 9;                         // warps 9-15: gathered rows, one whole 128-row slot at a time each
+constexpr int CH_A_WARPS = 7;
 constexpr int CH_DESC_WORDS = 48;                // sizeof(ConvDesc) / 4
 constexpr int CH_MAX_LAYERS = 16;                // layers per launch: the descriptors travel as kernel parameters (3 KB)
 
@@ -66,7 +68,7 @@ struct __align__(16) ConvDesc {
   int K, nb0, nb1;
   int cout, cout_pad, nt, n_ntiles;
   int relu, cmap_cout, nsplit, m_tiles;
-  int nsub_max;                    // sub-tiles per item that may share a weight tile: 2 when nt <= 128, else 1
+  int nsub_max;                    // sub-tiles per item that may share a weight tile: 4 when nt <= 128, else 2 (512 TMEM columns)
   int barrier_before;              // grid barrier before this layer (it reads what an earlier layer of the launch wrote)
   int stages_per_split;            // ceil(K * (nb0 + nb1) / nsplit)
   int pad[8];
@@ -189,13 +191,13 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
   long long pw0 = 0, pw1 = 0, pw2 = 0, pt = 0;     // cycles in this role's waits (up to three kinds) and in its loop
   if (dbg_clock && tid == 0) dbg_clock[blockIdx.x * 32 + 0] = clock64();
   uint32_t fullA = smem_u32(bars), emptyA = fullA + 12 * 8, fullB = fullA + 24 * 8, emptyB = fullA + 28 * 8;
-  uint32_t accFull = fullA + 32 * 8, accEmpty = fullA + 34 * 8, turnBar = fullA + 36 * 8;
-  CH_KEEP(fullA); CH_KEEP(emptyA); CH_KEEP(fullB); CH_KEEP(emptyB); CH_KEEP(accFull); CH_KEEP(accEmpty); CH_KEEP(turnBar);
+  uint32_t accFull = fullA + 32 * 8, accEmpty = fullA + 36 * 8;
+  CH_KEEP(fullA); CH_KEEP(emptyA); CH_KEEP(fullB); CH_KEEP(emptyB); CH_KEEP(accFull); CH_KEEP(accEmpty);
 
   if (tid == 0) {
     for (int s = 0; s < sa; ++s) { mbar_init(fullA + 8 * s, 32); mbar_init(emptyA + 8 * s, 1); }   // fullA: the 32 lanes of the slot's warp
-    for (int s = 0; s < sb; ++s) { mbar_init(fullB + 8 * s, 1); mbar_init(emptyB + 8 * s, 2); }   // emptyB: one arrival per issuer
-    for (int b = 0; b < 2; ++b) { mbar_init(accFull + 8 * b, 2); mbar_init(accEmpty + 8 * b, 4); mbar_init(turnBar + 8 * b, 1); }
+    for (int s = 0; s < sb; ++s) { mbar_init(fullB + 8 * s, 1); mbar_init(emptyB + 8 * s, CH_MMA_WARPS); }   // emptyB: one arrival per issuer
+    for (int b = 0; b < 4; ++b) { mbar_init(accFull + 8 * b, 1); mbar_init(accEmpty + 8 * b, 4); }   // per sub-tile accumulator
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == CH_W_MMA) {   // all 512 TMEM columns: two accumulator buffers of 256 columns (one CTA per SM, no contention)
@@ -213,8 +215,8 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
   if (dbg_clock && tid == 0) dbg_clock[blockIdx.x * 32 + 1] = clock64();
 
   // pipeline state of this thread's role; persists over items and layers
-  uint32_t a_slot = 0, a_phase = 0, b_slot = 0, b_phase = 0, n_item = 0;
-  uint32_t n_turn = 0;                             // MMA issuers: batches issued so far (token protocol below)
+  uint32_t a_slot = 0, a_phase = 0, b_slot = 0, b_phase = 0;
+  uint32_t use_bits = 0;                           // parity of the uses of accumulator s (bit s): issuers track their own, the epilogue all four
   uint32_t g_slot = 0;                             // gather producers: row slots the CTA has gone through (slot g belongs to warp g % CH_A_WARPS)
 
   for (int L = 0; L < n_layers; ++L) {
@@ -248,7 +250,7 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
 #define CH_FOR_ITEMS()                                                                                         \
     for (int64_t u = u_begin, _n; u < u_end; u += _n)                                                          \
       if (const int z = (int)(u / per_z), r_ = (int)(u - (int64_t)z * per_z), nti = r_ / d_m_tiles,            \
-          m = r_ - nti * d_m_tiles, nsub = (d_nsub_max == 2 && u + 1 < u_end && m + 1 < d_m_tiles) ? 2 : 1,    \
+          m = r_ - nti * d_m_tiles, nsub = (int)min((int64_t)min(d_nsub_max, d_m_tiles - m), u_end - u),        \
           t_begin = min(z * d_sps, T), t_end = min(t_begin + d_sps, T);                                        \
           (_n = nsub, true))
 
@@ -273,46 +275,30 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
           if (++b_slot == (uint32_t)sb) { b_slot = 0; b_phase ^= 1; }
         }
       }
-    } else if (warp == CH_W_MMA || warp == CH_W_MMA + 1) {
-      // ============ MMA issuers: warp CH_W_MMA owns sub-tile 0 of every item, the next warp sub-tile 1 ===============
-      // One issuing thread spends ~64 cycles per tcgen05.mma plus ~400 cycles of barrier-wait / fence / commit per row
-      // slot, more than the 288 cycles of tensor work a 96-channel slot carries; two issuers on disjoint accumulator
-      // columns restore the slack two co-resident CTAs used to give.  Each sub-tile's MMAs are issued by one thread, in
-      // stage order (bit-reproducible accumulation).
+    } else if (warp >= CH_W_MMA && warp < CH_W_MMA + CH_MMA_WARPS) {
+      // ============ MMA issuers: warp CH_W_MMA + i owns sub-tile i of every item ===============
+      // Measured (profiles/r02_chain_roles.md): one thread issues one tcgen05.mma per ~90 cycles and pays ~300 cycles of
+      // barrier probe / proxy fence / descriptor set-up / commit per row slot, i.e. ~830 cycles per slot against 288 cycles
+      // of tensor work (M128 x N96 x K16 x 6).  Only concurrent issue streams fill the pipe: up to four sub-tiles of an item
+      // are issued by four threads on disjoint accumulator columns, each in stage order (bit-reproducible accumulation).
       const int mi = warp - CH_W_MMA;
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(d_nt >> 3) << 17) | ((uint32_t)(CH_M >> 4) << 24);
+      const uint32_t dcol = tmem_base + (uint32_t)mi * (d_nt > 128 ? 256u : 128u);
       CH_FOR_ITEMS() {
         (void)m; (void)nti;
-        const uint32_t buf = n_item & 1u;
         const bool mine = mi < nsub;
-        // Both issuers follow the full protocol of every item, also the one without a sub-tile of its own (single-sub-tile
-        // items): its arrivals on emptyB / accFull may only happen in the phase they belong to, i.e. after the same waits.
-        { CH_PROF_BEGIN(); mbar_wait(accEmpty + 8 * buf, ((n_item >> 1) & 1u) ^ 1u); CH_PROF_END(pw2); }   // the epilogue drained this buffer
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t dcol = tmem_base + buf * 256u + (uint32_t)mi * 128u;
-        // two stages per iteration: the fixed cost of an iteration (waits, proxy fence, election, descriptor set-up) is a
-        // dependent chain of a few hundred cycles; 12 MMAs behind it instead of 6
-        for (int t = t_begin; t < t_end;) {
-          const int nst = min(2, t_end - t);
-          uint32_t sl[2], sph[2], bs[2], bph[2];
-          {
-            uint32_t as_ = a_slot + (uint32_t)mi, ap_ = a_phase, bs_ = b_slot, bp_ = b_phase;
-            if (as_ >= (uint32_t)sa) { as_ -= (uint32_t)sa; ap_ ^= 1u; }
-#pragma unroll
-            for (int jx = 0; jx < 2; ++jx) {
-              sl[jx] = as_; sph[jx] = ap_; bs[jx] = bs_; bph[jx] = bp_;
-              as_ += (uint32_t)nsub; if (as_ >= (uint32_t)sa) { as_ -= (uint32_t)sa; ap_ ^= 1u; }
-              if (++bs_ == (uint32_t)sb) { bs_ = 0; bp_ ^= 1u; }
-            }
-          }
+        if (mine) {                                   // the epilogue drained my accumulator (previous use)
+          CH_PROF_BEGIN(); mbar_wait(accEmpty + 8 * (uint32_t)mi, (use_bits & 1u) ^ 1u); CH_PROF_END(pw2);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        for (int t = t_begin; t < t_end; ++t) {
           if (mine) {
-            {                                         // all barriers of the batch probed together (overlapping round trips)
+            uint32_t sl = a_slot + (uint32_t)mi, ph = a_phase;             // my row slot of this stage
+            if (sl >= (uint32_t)sa) { sl -= (uint32_t)sa; ph ^= 1u; }
+            {                                         // both barriers probed together (overlapping round trips)
               CH_PROF_BEGIN();
-              const bool two = nst == 2;
-              const uint32_t b1 = two ? bs[1] : bs[0], bp1 = two ? bph[1] : bph[0], a1 = two ? sl[1] : sl[0], ap1 = two ? sph[1] : sph[0];
               for (uint32_t it = 0;; ++it) {
-                const uint32_t ok = mbar_try(fullB + 8 * bs[0], bph[0]) & mbar_try(fullA + 8 * sl[0], sph[0]) &
-                                    mbar_try(fullB + 8 * b1, bp1) & mbar_try(fullA + 8 * a1, ap1);
+                const uint32_t ok = mbar_try(fullB + 8 * b_slot, b_phase) & mbar_try(fullA + 8 * sl, ph);
                 if (ok) break;
                 if (it > (1u << 26)) __trap();
               }
@@ -320,67 +306,38 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) writes -> UMMA reads
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // The issuers take turns on the tensor pipe: tcgen05.mma issue blocks while the pipe's queue is full, so two
-            // threads issuing at the same time each take twice as long and the pipe idles while both do their set-up.
-            // Issuer 0 goes first; each passes the turn on after the first stage of its batch (the rest of its MMAs cover
-            // the other's wake-up).  Accumulators are disjoint, each is fed by one thread in stage order.
-            if (!(flags & 0x8000)) { CH_PROF_BEGIN(); mbar_wait(turnBar + 8 * (uint32_t)mi, mi == 0 ? ((n_turn & 1u) ^ 1u) : (n_turn & 1u)); CH_PROF_END(pw0); }
             if (flags & 0x4000) {                     // tuning: plain arrivals instead of tcgen05.commit (only without MMAs)
-              if (lane == 0) {
-#pragma unroll
-                for (int jx = 0; jx < 2; ++jx)
-                  if (jx < nst) { mbar_arrive(emptyA + 8 * sl[jx]); mbar_arrive(emptyB + 8 * bs[jx]); }
-              }
+              if (lane == 0) { mbar_arrive(emptyA + 8 * sl); mbar_arrive(emptyB + 8 * b_slot); }
             } else if (elect_one()) {
+              const uint64_t db = umma_desc(b_ring_k + b_slot * (uint32_t)bslot);
+              const uint64_t da = umma_desc(a_ring_k + sl * (uint32_t)CH_A_BYTES);
+              // 128-byte line = [hi ch0-15 | hi ch16-31 | lo ch0-15 | lo ch16-31]; +2 per 32-byte K slice
 #pragma unroll
-              for (int jx = 0; jx < 2; ++jx) {
-                if (jx < nst) {
-                  const uint64_t db = umma_desc(b_ring_k + bs[jx] * (uint32_t)bslot);
-                  const uint64_t da = umma_desc(a_ring_k + sl[jx] * (uint32_t)CH_A_BYTES);
-                  // 128-byte line = [hi ch0-15 | hi ch16-31 | lo ch0-15 | lo ch16-31]; +2 per 32-byte K slice
-#pragma unroll
-                  for (int h = 0; h < 2; ++h) {
-                    if (flags & 0x400) break;         // tuning: no MMAs
-                    umma_bf16(dcol, da + 2 * h, db + 2 * h, idesc, (h == 0 && jx == 0 && t == t_begin) ? 0u : 1u);   // hi * Whi
-                    umma_bf16(dcol, da + 2 * h, db + 2 * h + 4, idesc, 1u);                                          // hi * Wlo
-                    umma_bf16(dcol, da + 2 * h + 4, db + 2 * h, idesc, 1u);                                          // lo * Whi
-                  }
-                  umma_commit(emptyA + 8 * sl[jx]);                         // row slot free when these MMAs retire
-                  umma_commit(emptyB + 8 * bs[jx]);                         // weight slot: one arrival per issuer
-                  if (jx == 0 && !(flags & 0x8000)) mbar_arrive(turnBar + 8 * (uint32_t)(1 - mi));   // pass the turn on
-                }
+              for (int h = 0; h < 2; ++h) {
+                if (flags & 0x400) break;             // tuning: no MMAs
+                umma_bf16(dcol, da + 2 * h, db + 2 * h, idesc, (h == 0 && t == t_begin) ? 0u : 1u);   // hi * Whi
+                umma_bf16(dcol, da + 2 * h, db + 2 * h + 4, idesc, 1u);                                // hi * Wlo
+                umma_bf16(dcol, da + 2 * h + 4, db + 2 * h, idesc, 1u);                                // lo * Whi
               }
+              umma_commit(emptyA + 8 * sl);                                 // row slot free when these MMAs retire
+              umma_commit(emptyB + 8 * b_slot);                             // weight slot: one arrival per issuer
             }
-            if ((flags & 0x4000) && !(flags & 0x8000) && lane == 0) mbar_arrive(turnBar + 8 * (uint32_t)(1 - mi));
           } else {
-#pragma unroll
-            for (int jx = 0; jx < 2; ++jx) {
-              if (jx < nst) {
-                mbar_wait(fullB + 8 * bs[jx], bph[jx]);                     // stay in step with the slot's phase ...
-                if (lane == 0) mbar_arrive(emptyB + 8 * bs[jx]);            // ... nothing of mine reads this weight tile
-              }
-            }
-            if (!(flags & 0x8000)) {                  // keep the turn protocol going (one wait, one hand-over per batch)
-              mbar_wait(turnBar + 8 * (uint32_t)mi, mi == 0 ? ((n_turn & 1u) ^ 1u) : (n_turn & 1u));
-              if (lane == 0) mbar_arrive(turnBar + 8 * (uint32_t)(1 - mi));
-            }
+            // No sub-tile of mine in this item: still one arrival per weight slot, and only in the phase it belongs to
+            // (the slot's full barrier of this stage has completed).
+            mbar_wait(fullB + 8 * b_slot, b_phase);
+            if (lane == 0) mbar_arrive(emptyB + 8 * b_slot);
           }
           __syncwarp();
-          ++n_turn;
-#pragma unroll
-          for (int jx = 0; jx < 2; ++jx) {
-            if (jx < nst) {
-              a_slot += (uint32_t)nsub;
-              if (a_slot >= (uint32_t)sa) { a_slot -= (uint32_t)sa; a_phase ^= 1u; }
-              if (++b_slot == (uint32_t)sb) { b_slot = 0; b_phase ^= 1; }
-            }
-          }
-          t += nst;
+          a_slot += (uint32_t)nsub;
+          if (a_slot >= (uint32_t)sa) { a_slot -= (uint32_t)sa; a_phase ^= 1u; }
+          if (++b_slot == (uint32_t)sb) { b_slot = 0; b_phase ^= 1; }
         }
-        if (mine) { if (elect_one()) umma_commit(accFull + 8 * buf); }
-        else if (lane == 0) mbar_arrive(accFull + 8 * buf);
-        __syncwarp();
-        ++n_item;
+        if (mine) {
+          if (elect_one()) umma_commit(accFull + 8 * (uint32_t)mi);
+          __syncwarp();
+          use_bits ^= 1u;
+        }
       }
     } else if (warp >= CH_W_A) {
       // ================= gathered A rows: warp w fills every CH_A_WARPS-th row slot, all 128 rows of it ====================
@@ -400,8 +357,9 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
         // my slots of this item: local indices jl with (g_slot + jl) % CH_A_WARPS == w, where g_slot counts the CTA's slots
         int jl = (int)((uint32_t)(w + CH_A_WARPS - (int)(g_slot % CH_A_WARPS)) % CH_A_WARPS);
         auto decode = [&](int jl_, int &k_, int &cb_, int &s_) {
-          const int tt = t_begin + (nsub == 2 ? (jl_ >> 1) : jl_);
-          s_ = nsub == 2 ? (jl_ & 1) : 0;
+          const int st = jl_ / nsub;                  // stage-major, sub-tile-minor: the order the issuers consume slots in
+          s_ = jl_ - st * nsub;
+          const int tt = t_begin + st;
           k_ = tt / nb; cb_ = tt - k_ * nb;
         };
         auto fetch = [&](int k_, int s_, int32_t (&r)[4]) {
@@ -436,10 +394,17 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
           const uint32_t a_dst = a_ring_k + sl * (uint32_t)CH_A_BYTES;
           if (!(flags & 0x100)) {                     // tuning: bit 8 = no row copies
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {            // rows 4i + q
-              const int32_t r = __shfl_sync(0xffffffffu, cur[i >> 3], (4 * i + q) & 31);
-              const uint32_t rr = r < 0 ? 0u : (uint32_t)r;
-              cp_async16_zfill(a_dst + (uint32_t)(i >> 1) * 1024u + ((i & 1) ? off_odd : off_even), src + (uint64_t)rr * rb, r < 0 ? 1u : 0u);
+            for (int g8 = 0; g8 < 4; ++g8) {          // 8 copy instructions at a time: shuffles first, then the copies
+              int32_t r8[8];
+#pragma unroll
+              for (int ii = 0; ii < 8; ++ii) r8[ii] = __shfl_sync(0xffffffffu, cur[g8], (4 * ii + q) & 31);   // rows 32 g8 + 4 ii + q
+#pragma unroll
+              for (int ii = 0; ii < 8; ++ii) {
+                const int i = g8 * 8 + ii;
+                const uint32_t rr = r8[ii] < 0 ? 0u : (uint32_t)r8[ii];
+                cp_async16_zfill(a_dst + (uint32_t)(i >> 1) * 1024u + ((i & 1) ? off_odd : off_even), src + (uint64_t)rr * rb,
+                                 r8[ii] < 0 ? 1u : 0u);
+              }
             }
           }
           cp_async_arrive_noinc(fullA + 8 * sl);      // 32 self-tracking arrivals, fired by the copy engine
@@ -467,11 +432,11 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
       const int32_t *d_row_map = s_desc->out_row_map, *d_cmap = s_desc->cmap;
       auto lds128 = [](uint32_t a) { uint4 v; asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; };
       auto sts128 = [](uint32_t a, uint4 v) { asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); };
+      const uint32_t sub_cols = d_nt > 128 ? 256u : 128u;
       CH_FOR_ITEMS() {
-        const uint32_t buf = n_item & 1u;
-        { CH_PROF_BEGIN(); mbar_wait_relaxed(accFull + 8 * buf, (n_item >> 1) & 1u, 128); CH_PROF_END(pw0); }
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int s = 0; s < nsub; ++s) {
+          { CH_PROF_BEGIN(); mbar_wait_relaxed(accFull + 8 * (uint32_t)s, (use_bits >> s) & 1u, 64); CH_PROF_END(pw0); }
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const int64_t wrow0 = (int64_t)(m + s) * CH_M + q * 32;        // first global row of this warp
           const int64_t o = wrow0 + lane;
           int32_t my_orow = (int32_t)min(o, d_n_out - 1);
@@ -497,7 +462,7 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
             float y[32];
             {
               uint32_t v0[16], v1[16];
-              const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256u + (uint32_t)s * 128u + cbo * 32;
+              const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)s * sub_cols + cbo * 32;
               tmem_ld16(taddr, v0);
               tmem_ld16(taddr + 16, v1);
               asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -576,12 +541,12 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
               __syncwarp();
             }
           }
+          // this warp's TMEM reads of the sub-tile are complete (tcgen05.wait::ld above): hand it back to its issuer
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(accEmpty + 8 * (uint32_t)s);
+          use_bits ^= 1u << s;
         }
-        // this warp's TMEM reads of the buffer are complete (tcgen05.wait::ld above): hand it back to the MMA warps
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(accEmpty + 8 * buf);
-        ++n_item;
       }
     }
 #undef CH_FOR_ITEMS
@@ -706,7 +671,7 @@ static int chain_nsplit(int64_t n_out, int K, int cin, int cout, int grid_ctas, 
 }
 
 static int g_chain_force_split = 0;      // tuning: > 0 forces the split factor of every layer (1 disables splitting)
-static int g_chain_nsub = 2;             // tuning: 1 = never pair sub-tiles
+static int g_chain_nsub = 4;             // tuning: most sub-tiles per item (1 = never share a weight tile)
 static int g_chain_grid = 0;             // tuning: CTAs per launch (0 = one per SM)
 static int g_chain_sa = 0, g_chain_sb = 0;   // tuning: ring depths (0 = as many row slots as fit / 3 or 2 weight slots)
 static long long *g_chain_dbg_clock = nullptr;
@@ -761,7 +726,7 @@ int osb_conv_desc_fill(void *desc_host, const void *src0, int32_t c0, const void
   d.out_row_map = out_row_map; d.cmap = cmap; d.n_out = n_out; d.K = K; d.nb0 = c0 / 32; d.nb1 = c1 / 32;
   d.cout = cout; d.cout_pad = chain_cout_pad(cout); d.nt = chain_nt(cout); d.n_ntiles = d.cout_pad / d.nt;
   d.relu = relu; d.cmap_cout = cmap_cout; d.m_tiles = (int)ceil_div(n_out, CH_M);
-  d.nsub_max = (d.nt <= 128 && g_chain_nsub >= 2) ? 2 : 1;
+  d.nsub_max = std::max(1, std::min(g_chain_nsub, d.nt <= 128 ? 4 : 2));
   d.barrier_before = barrier_before ? 1 : 0;
   d.nsplit = cmap ? 1 : chain_nsplit(n_out, K, cin, cout, osb_conv_chain_grid(), g_chain_force_split);
   const int T = K * (cin / 32);
