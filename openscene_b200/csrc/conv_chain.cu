@@ -86,6 +86,40 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// one non-blocking-ish probe of an mbarrier phase (true = complete).  Several probes issued back to back overlap their
+// ~190-cycle round trips; a chain of mbar_wait calls pays them one after the other.
+__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done;
+}
+
+// A wait that never completes must not hang the GPU: after ~2^24 probes the thread reports where it is stuck into the
+// tuning buffer (if one is set; use pinned host memory so that the report survives the trap) and traps.
+__device__ long long *g_chain_report = nullptr;
+__device__ __noinline__ void chain_stuck(uint32_t bar, uint32_t parity, int tag) {
+  long long *r = g_chain_report;
+  if (r) {
+    long long *o = r + 1 + 4 * ((blockIdx.x * 16 + (threadIdx.x >> 5)) % 1024);
+    o[0] = ((long long)blockIdx.x << 32) | (threadIdx.x >> 5); o[1] = bar; o[2] = parity; o[3] = tag;
+    r[0] = 1;
+    __threadfence_system();
+  }
+  __trap();
+}
+__device__ __forceinline__ void chain_wait(uint32_t bar, uint32_t parity, int tag) {
+  for (uint32_t it = 0;; ++it) {
+    if (mbar_try(bar, parity)) return;
+    if (it > (1u << 22)) chain_stuck(bar, parity, tag);
+  }
+}
+
 // wait of a role with slack (epilogue, weight producer): back off between polls so that the polling does not take issue slots
 // from the roles on the critical path
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, unsigned sleep_ns) {
@@ -137,20 +171,6 @@ __device__ __forceinline__ void grid_barrier(unsigned *gbar, unsigned &gen) {
 // per-role cycle accounting (tuning; active only when a clock buffer is given): dbg_clock[cta*32 + slot]
 #define CH_PROF_BEGIN() const long long _t0 = prof ? clock64() : 0
 #define CH_PROF_END(var) do { if (prof) var += clock64() - _t0; } while (0)
-
-// one non-blocking-ish probe of an mbarrier phase (true = complete).  Several probes issued back to back overlap their
-// ~190-cycle round trips; a chain of mbar_wait calls pays them one after the other.
-__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(done)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return done;
-}
 
 // keep a value in its register: stops the compiler from re-deriving shared-window addresses (S2R + shifts) in hot loops
 #define CH_KEEP(x) asm volatile("" : "+r"(x))
@@ -261,7 +281,7 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
       CH_FOR_ITEMS() {
         (void)m;
         for (int t = t_begin; t < t_end; ++t) {
-          { CH_PROF_BEGIN(); mbar_wait_relaxed(emptyB + 8 * b_slot, b_phase ^ 1, 64); CH_PROF_END(pw0); }
+          { CH_PROF_BEGIN(); chain_wait(emptyB + 8 * b_slot, b_phase ^ 1, 5 | (t << 8)); CH_PROF_END(pw0); }
           if (elect_one()) {
             const uint32_t fb = fullB + 8 * b_slot;
             if (flags & 0x200) {                      // tuning: no weight loads
@@ -288,7 +308,7 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
         (void)m; (void)nti;
         const bool mine = mi < nsub;
         if (mine) {                                   // the epilogue drained my accumulator (previous use)
-          CH_PROF_BEGIN(); mbar_wait(accEmpty + 8 * (uint32_t)mi, (use_bits & 1u) ^ 1u); CH_PROF_END(pw2);
+          CH_PROF_BEGIN(); chain_wait(accEmpty + 8 * (uint32_t)mi, (use_bits & 1u) ^ 1u, 1); CH_PROF_END(pw2);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         for (int t = t_begin; t < t_end; ++t) {
@@ -300,7 +320,7 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
               for (uint32_t it = 0;; ++it) {
                 const uint32_t ok = mbar_try(fullB + 8 * b_slot, b_phase) & mbar_try(fullA + 8 * sl, ph);
                 if (ok) break;
-                if (it > (1u << 26)) __trap();
+                if (it > (1u << 22)) chain_stuck(fullA + 8 * sl, ph, 2 | (mbar_try(fullB + 8 * b_slot, b_phase) ? 0 : 16) | (t << 8));
               }
               CH_PROF_END(pw1);
             }
@@ -325,7 +345,7 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
           } else {
             // No sub-tile of mine in this item: still one arrival per weight slot, and only in the phase it belongs to
             // (the slot's full barrier of this stage has completed).
-            mbar_wait(fullB + 8 * b_slot, b_phase);
+            chain_wait(fullB + 8 * b_slot, b_phase, 3);
             if (lane == 0) mbar_arrive(emptyB + 8 * b_slot);
           }
           __syncwarp();
@@ -390,7 +410,7 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
           const bool first = cb < d_nb0;
           const uint8_t *src = (first ? src0 : src1) + (first ? cb : cb - d_nb0) * 128;
           const uint32_t rb = first ? rb0 : rb1;
-          { CH_PROF_BEGIN(); mbar_wait(emptyA + 8 * sl, ph ^ 1); CH_PROF_END(pw0); }
+          { CH_PROF_BEGIN(); chain_wait(emptyA + 8 * sl, ph ^ 1, 4 | (jl << 8)); CH_PROF_END(pw0); }
           const uint32_t a_dst = a_ring_k + sl * (uint32_t)CH_A_BYTES;
           if (!(flags & 0x100)) {                     // tuning: bit 8 = no row copies
 #pragma unroll
@@ -435,7 +455,7 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
       const uint32_t sub_cols = d_nt > 128 ? 256u : 128u;
       CH_FOR_ITEMS() {
         for (int s = 0; s < nsub; ++s) {
-          { CH_PROF_BEGIN(); mbar_wait_relaxed(accFull + 8 * (uint32_t)s, (use_bits >> s) & 1u, 64); CH_PROF_END(pw0); }
+          { CH_PROF_BEGIN(); chain_wait(accFull + 8 * (uint32_t)s, (use_bits >> s) & 1u, 6 | (s << 8)); CH_PROF_END(pw0); }
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const int64_t wrow0 = (int64_t)(m + s) * CH_M + q * 32;        // first global row of this warp
           const int64_t o = wrow0 + lane;
@@ -687,6 +707,10 @@ int osb_tuning_set(const char *name, int64_t value) {
   else if (n == "chain_sb") g_chain_sb = (int)value;
   else if (n == "chain_dbg_clock") g_chain_dbg_clock = (long long *)(intptr_t)value;
   else if (n == "chain_dbg_skip") g_chain_dbg_skip = (int)value;
+  else if (n == "chain_report") {               // host-mapped int64 buffer [1 + 4*1024]: where a stuck wait was (tuning)
+    long long *ptr = (long long *)(intptr_t)value;
+    OSB_CUDA(cudaMemcpyToSymbol(g_chain_report, &ptr, sizeof(ptr)));
+  }
   else { OSB_CHECK(conv_tc_tuning(n.c_str(), value), "osb_tuning_set: unknown knob '%s'", n.c_str()); }
   return 0;
 }
