@@ -270,7 +270,8 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
 #define CH_FOR_ITEMS()                                                                                         \
     for (int64_t u = u_begin, _n; u < u_end; u += _n)                                                          \
       if (const int z = (int)(u / per_z), r_ = (int)(u - (int64_t)z * per_z), nti = r_ / d_m_tiles,            \
-          m = r_ - nti * d_m_tiles, nsub = (int)min((int64_t)min(d_nsub_max, d_m_tiles - m), u_end - u),        \
+          m = r_ - nti * d_m_tiles, nsub_ = (int)min((int64_t)min(d_nsub_max, d_m_tiles - m), u_end - u),       \
+          nsub = nsub_ == 3 ? 2 : nsub_,   /* items of 1, 2 or 4 sub-tiles (3 hung on hardware: see DESIGN.md) */  \
           t_begin = min(z * d_sps, T), t_end = min(t_begin + d_sps, T);                                        \
           (_n = nsub, true))
 
