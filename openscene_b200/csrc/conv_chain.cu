@@ -203,7 +203,7 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
   uint8_t *aux = smem + (stg_u32 - base_u32) + CH_STG_BYTES;
   float *s_ss = reinterpret_cast<float *>(aux);                              // [scale x CH_SS_FLOATS | shift x CH_SS_FLOATS]
   uint64_t *bars = reinterpret_cast<uint64_t *>(s_ss + 2 * CH_SS_FLOATS);
-  uint32_t *s_misc = reinterpret_cast<uint32_t *>(bars + 40);                // [0] TMEM base
+  uint32_t *s_misc = reinterpret_cast<uint32_t *>(bars + 44);                // [0] TMEM base
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (flags & 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -211,13 +211,14 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
   long long pw0 = 0, pw1 = 0, pw2 = 0, pt = 0;     // cycles in this role's waits (up to three kinds) and in its loop
   if (dbg_clock && tid == 0) dbg_clock[blockIdx.x * 32 + 0] = clock64();
   uint32_t fullA = smem_u32(bars), emptyA = fullA + 12 * 8, fullB = fullA + 24 * 8, emptyB = fullA + 28 * 8;
-  uint32_t accFull = fullA + 32 * 8, accEmpty = fullA + 36 * 8;
-  CH_KEEP(fullA); CH_KEEP(emptyA); CH_KEEP(fullB); CH_KEEP(emptyB); CH_KEEP(accFull); CH_KEEP(accEmpty);
+  uint32_t accFull = fullA + 32 * 8, accEmpty = fullA + 36 * 8, stageBar = fullA + 40 * 8;
+  CH_KEEP(fullA); CH_KEEP(emptyA); CH_KEEP(fullB); CH_KEEP(emptyB); CH_KEEP(accFull); CH_KEEP(accEmpty); CH_KEEP(stageBar);
 
   if (tid == 0) {
     for (int s = 0; s < sa; ++s) { mbar_init(fullA + 8 * s, 32); mbar_init(emptyA + 8 * s, 1); }   // fullA: the 32 lanes of the slot's warp
     for (int s = 0; s < sb; ++s) { mbar_init(fullB + 8 * s, 1); mbar_init(emptyB + 8 * s, CH_MMA_WARPS); }   // emptyB: one arrival per issuer
     for (int b = 0; b < 4; ++b) { mbar_init(accFull + 8 * b, 1); mbar_init(accEmpty + 8 * b, 4); }   // per sub-tile accumulator
+    for (int b = 0; b < 2; ++b) mbar_init(stageBar + 8 * b, CH_MMA_WARPS);                          // issuer skew limiter
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == CH_W_MMA) {   // all 512 TMEM columns: two accumulator buffers of 256 columns (one CTA per SM, no contention)
@@ -236,8 +237,10 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
 
   // pipeline state of this thread's role; persists over items and layers
   uint32_t a_slot = 0, a_phase = 0, b_slot = 0, b_phase = 0;
+  uint32_t n_stage = 0;                            // MMA issuers: stages gone through (skew limiter below)
   uint32_t use_bits = 0;                           // parity of the uses of accumulator s (bit s): issuers track their own, the epilogue all four
-  uint32_t g_slot = 0;                             // gather producers: row slots the CTA has gone through (slot g belongs to warp g % CH_A_WARPS)
+  uint32_t g_slot = 0;                             // gather producers: row slots the CTA has gone through before the current item
+  uint32_t p_sl = warp >= CH_W_A ? (uint32_t)(warp - CH_W_A) : 0u, p_lapb = 0, p_par = 0;   // gather producers: my next ring slot, global index of slot 0 of its lap, lap parity
 
   for (int L = 0; L < n_layers; ++L) {
     __syncthreads();                                   // every role is done with the previous layer (and with s_ss)
@@ -270,8 +273,7 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
 #define CH_FOR_ITEMS()                                                                                         \
     for (int64_t u = u_begin, _n; u < u_end; u += _n)                                                          \
       if (const int z = (int)(u / per_z), r_ = (int)(u - (int64_t)z * per_z), nti = r_ / d_m_tiles,            \
-          m = r_ - nti * d_m_tiles, nsub_ = (int)min((int64_t)min(d_nsub_max, d_m_tiles - m), u_end - u),       \
-          nsub = nsub_ == 3 ? 2 : nsub_,   /* items of 1, 2 or 4 sub-tiles (3 hung on hardware: see DESIGN.md) */  \
+          m = r_ - nti * d_m_tiles, nsub = (int)min((int64_t)min(d_nsub_max, d_m_tiles - m), u_end - u),        \
           t_begin = min(z * d_sps, T), t_end = min(t_begin + d_sps, T);                                        \
           (_n = nsub, true))
 
@@ -313,13 +315,18 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         for (int t = t_begin; t < t_end; ++t) {
+          // Skew limiter.  The row ring is SHARED by the issuers (slot s is read by different issuers in different laps) and
+          // an mbarrier only tells phase parity: an issuer more than one lap ahead of the slowest one would mistake "lap L-2
+          // filled" for "lap L filled".  The weight ring alone allows a skew of sb - 1 = 2 stages, a lap of the row ring can be
+          // as short as sa / nsub = 2.5 stages.  No issuer starts stage n before all have finished stage n - 2.
+          const uint32_t sgb = stageBar + 8 * (n_stage & 1u), sgp = ((n_stage >> 1) & 1u) ^ 1u;
           if (mine) {
             uint32_t sl = a_slot + (uint32_t)mi, ph = a_phase;             // my row slot of this stage
             if (sl >= (uint32_t)sa) { sl -= (uint32_t)sa; ph ^= 1u; }
             {                                         // both barriers probed together (overlapping round trips)
               CH_PROF_BEGIN();
               for (uint32_t it = 0;; ++it) {
-                const uint32_t ok = mbar_try(fullB + 8 * b_slot, b_phase) & mbar_try(fullA + 8 * sl, ph);
+                const uint32_t ok = mbar_try(sgb, sgp) & mbar_try(fullB + 8 * b_slot, b_phase) & mbar_try(fullA + 8 * sl, ph);
                 if (ok) break;
                 if (it > (1u << 22)) chain_stuck(fullA + 8 * sl, ph, 2 | (mbar_try(fullB + 8 * b_slot, b_phase) ? 0 : 16) | (t << 8));
               }
@@ -346,10 +353,13 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
           } else {
             // No sub-tile of mine in this item: still one arrival per weight slot, and only in the phase it belongs to
             // (the slot's full barrier of this stage has completed).
+            chain_wait(sgb, sgp, 7);
             chain_wait(fullB + 8 * b_slot, b_phase, 3);
             if (lane == 0) mbar_arrive(emptyB + 8 * b_slot);
           }
           __syncwarp();
+          if (lane == 0) mbar_arrive(sgb);            // this stage is behind me (its MMAs are issued)
+          ++n_stage;
           a_slot += (uint32_t)nsub;
           if (a_slot >= (uint32_t)sa) { a_slot -= (uint32_t)sa; a_phase ^= 1u; }
           if (++b_slot == (uint32_t)sb) { b_slot = 0; b_phase ^= 1; }
@@ -372,14 +382,15 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
       const uint32_t rb0 = (uint32_t)d_nb0 * 128u, rb1 = (uint32_t)d_nb1 * 128u;
       const uint32_t off_even = (uint32_t)q * 128u + (uint32_t)((j ^ q) << 4);                 // rows 8n + q
       const uint32_t off_odd = (uint32_t)(4 + q) * 128u + (uint32_t)((j ^ (4 + q)) << 4);      // rows 8n + 4 + q
+      // Ring slot s is always filled by warp s % CH_A_WARPS, lap after lap: a warp cannot run a lap ahead of itself, so the
+      // parity of a slot's empty barrier is unambiguous (with slots dealt round-robin over the warps, a fast warp one lap
+      // ahead of a slow one passed the parity test early and overwrote rows that had not been multiplied yet).
       CH_FOR_ITEMS() {
         (void)nti;
-        const int n_slots = (t_end - t_begin) * nsub;
-        // my slots of this item: local indices jl with (g_slot + jl) % CH_A_WARPS == w, where g_slot counts the CTA's slots
-        int jl = (int)((uint32_t)(w + CH_A_WARPS - (int)(g_slot % CH_A_WARPS)) % CH_A_WARPS);
-        auto decode = [&](int jl_, int &k_, int &cb_, int &s_) {
-          const int st = jl_ / nsub;                  // stage-major, sub-tile-minor: the order the issuers consume slots in
-          s_ = jl_ - st * nsub;
+        const uint32_t n_slots = (uint32_t)((t_end - t_begin) * nsub), g_end = g_slot + n_slots;
+        auto decode = [&](uint32_t jl_, int &k_, int &cb_, int &s_) {
+          const int st = (int)jl_ / nsub;             // stage-major, sub-tile-minor: the order the issuers consume slots in
+          s_ = (int)jl_ - st * nsub;
           const int tt = t_begin + st;
           k_ = tt / nb; cb_ = tt - k_ * nb;
         };
@@ -393,8 +404,9 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
         };
         int32_t nxt[4];
         int k_n = 0, cb_n = 0, s_n = 0;
-        if (jl < n_slots) { decode(jl, k_n, cb_n, s_n); fetch(k_n, s_n, nxt); }
-        for (; jl < n_slots; jl += CH_A_WARPS) {
+        const bool owner = (uint32_t)w < (uint32_t)sa;
+        if (owner && p_lapb + p_sl < g_end) { decode(p_lapb + p_sl - g_slot, k_n, cb_n, s_n); fetch(k_n, s_n, nxt); }
+        while (owner && p_lapb + p_sl < g_end) {
           int32_t cur[4];
           {
             CH_PROF_BEGIN();
@@ -404,14 +416,15 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
             CH_PROF_END(pw1);
           }
           const int cb = cb_n;
-          if (jl + CH_A_WARPS < n_slots) { decode(jl + CH_A_WARPS, k_n, cb_n, s_n); fetch(k_n, s_n, nxt); }   // my next slot's indices
-          // ring slot / phase of local slot jl
-          const uint32_t lin = a_slot + (uint32_t)jl, wraps = lin / (uint32_t)sa;
-          const uint32_t sl = lin - wraps * (uint32_t)sa, ph = a_phase ^ (wraps & 1u);
+          const uint32_t sl = p_sl, par = p_par, jl = p_lapb + p_sl - g_slot;
+          // my next slot (same warp, CH_A_WARPS slots on or the next lap)
+          p_sl += CH_A_WARPS;
+          if (p_sl >= (uint32_t)sa) { p_sl = (uint32_t)w; p_lapb += (uint32_t)sa; p_par ^= 1u; }
+          if (p_lapb + p_sl < g_end) { decode(p_lapb + p_sl - g_slot, k_n, cb_n, s_n); fetch(k_n, s_n, nxt); }   // its row indices, ahead of time
           const bool first = cb < d_nb0;
           const uint8_t *src = (first ? src0 : src1) + (first ? cb : cb - d_nb0) * 128;
           const uint32_t rb = first ? rb0 : rb1;
-          { CH_PROF_BEGIN(); chain_wait(emptyA + 8 * sl, ph ^ 1, 4 | (jl << 8)); CH_PROF_END(pw0); }
+          { CH_PROF_BEGIN(); chain_wait(emptyA + 8 * sl, par ^ 1u, 4 | ((int)jl << 8)); CH_PROF_END(pw0); }
           const uint32_t a_dst = a_ring_k + sl * (uint32_t)CH_A_BYTES;
           if (!(flags & 0x100)) {                     // tuning: bit 8 = no row copies
 #pragma unroll
@@ -430,13 +443,7 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
           }
           cp_async_arrive_noinc(fullA + 8 * sl);      // 32 self-tracking arrivals, fired by the copy engine
         }
-        // every producer warp advances the shared view of the ring by the whole item
-        g_slot += (uint32_t)n_slots;
-        {
-          const uint32_t lin = a_slot + (uint32_t)n_slots, wraps = lin / (uint32_t)sa;
-          a_slot = lin - wraps * (uint32_t)sa;
-          a_phase ^= (wraps & 1u);
-        }
+        g_slot = g_end;
       }
     } else if (warp < 4) {
       // ================= epilogue: four warps drain both accumulator buffers in turn ====================
@@ -793,7 +800,7 @@ int osb_conv_chain_launch(const void *descs_host, int32_t n_layers, void *grid_b
     }
     OSB_CHECK(!need_bar || grid_barrier_dev != nullptr, "osb_conv_chain_launch: this chain needs the grid-barrier words");
     const int bslot = nt_max * 128;
-    const int fixed = 1024 + CH_STG_BYTES + 2 * CH_SS_FLOATS * 4 + 40 * 8 + 64;   // alignment slack, staging, BN constants, barriers
+    const int fixed = 1024 + CH_STG_BYTES + 2 * CH_SS_FLOATS * 4 + 44 * 8 + 64;   // alignment slack, staging, BN constants, barriers
     int sb = g_chain_sb > 0 ? g_chain_sb : (bslot >= 32768 ? 2 : 3);
     sb = std::min(sb, CH_MAX_SB);
     int sa = (227 * 1024 - fixed - sb * bslot) / CH_A_BYTES;
