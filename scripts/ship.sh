@@ -6,6 +6,6 @@ MSG="$1"; T="$2"; shift 2
 git -C /root/repo/.wt/dev add -A
 git -C /root/repo/.wt/dev commit -q -m "$MSG" || true
 git -C /root/repo merge -q dev
-(python -c "import __graft_entry__ as g; g.build()")
+(cd /root/repo && python -c "import __graft_entry__ as g; g.build()")
 git -C /root/repo log --oneline | head -1
 cd /root/repo && scripts/gpurun_retry.sh "$T" "$@"
