@@ -436,8 +436,11 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
               for (int ii = 0; ii < 8; ++ii) {
                 const int i = g8 * 8 + ii;
                 const uint32_t rr = r8[ii] < 0 ? 0u : (uint32_t)r8[ii];
-                cp_async16_zfill(a_dst + (uint32_t)(i >> 1) * 1024u + ((i & 1) ? off_odd : off_even), src + (uint64_t)rr * rb,
-                                 r8[ii] < 0 ? 1u : 0u);
+                // src-size form (16 or 0 bytes): the copy engine itself writes the zeros of a missing neighbour, so they are
+                // covered by the self-tracking arrival below.  (The ignore-src predicate form produced intermittently stale
+                // rows in the slot that is consumed right after it is filled: profiles/r02_chain_roles.md.)
+                cp_async16(a_dst + (uint32_t)(i >> 1) * 1024u + ((i & 1) ? off_odd : off_even), src + (uint64_t)rr * rb,
+                           r8[ii] < 0 ? 0u : 16u);
               }
             }
           }
