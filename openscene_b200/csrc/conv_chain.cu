@@ -215,7 +215,7 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
   CH_KEEP(fullA); CH_KEEP(emptyA); CH_KEEP(fullB); CH_KEEP(emptyB); CH_KEEP(accFull); CH_KEEP(accEmpty); CH_KEEP(stageBar);
 
   if (tid == 0) {
-    for (int s = 0; s < sa; ++s) { mbar_init(fullA + 8 * s, 32); mbar_init(emptyA + 8 * s, 1); }   // fullA: the 32 lanes of the slot's warp
+    for (int s = 0; s < sa; ++s) { mbar_init(fullA + 8 * s, 1); mbar_init(emptyA + 8 * s, 1); }    // fullA: one arrival by the slot's warp
     for (int s = 0; s < sb; ++s) { mbar_init(fullB + 8 * s, 1); mbar_init(emptyB + 8 * s, CH_MMA_WARPS); }   // emptyB: one arrival per issuer
     for (int b = 0; b < 4; ++b) { mbar_init(accFull + 8 * b, 1); mbar_init(accEmpty + 8 * b, 4); }   // per sub-tile accumulator
     for (int b = 0; b < 2; ++b) mbar_init(stageBar + 8 * b, CH_MMA_WARPS);                          // issuer skew limiter
@@ -332,7 +332,6 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
               }
               CH_PROF_END(pw1);
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) writes -> UMMA reads
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (flags & 0x4000) {                     // tuning: plain arrivals instead of tcgen05.commit (only without MMAs)
               if (lane == 0) { mbar_arrive(emptyA + 8 * sl); mbar_arrive(emptyB + 8 * b_slot); }
@@ -444,7 +443,15 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
               }
             }
           }
-          cp_async_arrive_noinc(fullA + 8 * sl);      // 32 self-tracking arrivals, fired by the copy engine
+          // Completion on the WRITER side (the documented cross-proxy pattern): wait for my copies, make them visible to the
+          // async proxy the tensor core reads shared memory through, then one arrival per warp.  The self-tracking
+          // `cp.async.mbarrier.arrive.noinc` + a proxy fence on the consumer side (first-generation kernel) let the slot that
+          // is multiplied right after it lands be read stale now and then (profiles/r02_chain_roles.md, item 5).
+          asm volatile("cp.async.commit_group;" ::: "memory");
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(fullA + 8 * sl);
         }
         g_slot = g_end;
       }
