@@ -103,20 +103,20 @@ __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
 // A wait that never completes must not hang the GPU: after ~2^24 probes the thread reports where it is stuck into the
 // tuning buffer (if one is set; use pinned host memory so that the report survives the trap) and traps.
 __device__ long long *g_chain_report = nullptr;
-__device__ __noinline__ void chain_stuck(uint32_t bar, uint32_t parity, int tag) {
+__device__ __noinline__ void chain_stuck(uint32_t bar, uint32_t parity, int tag, uint32_t it) {
   long long *r = g_chain_report;
-  if (r) {
+  if (r && it == (1u << 20) + 1) {               // report once, keep waiting so that the other stuck roles can report too
     long long *o = r + 1 + 4 * ((blockIdx.x * 16 + (threadIdx.x >> 5)) % 1024);
     o[0] = ((long long)blockIdx.x << 32) | (threadIdx.x >> 5); o[1] = bar; o[2] = parity; o[3] = tag;
     r[0] = 1;
     __threadfence_system();
   }
-  __trap();
+  if (it > (1u << 23) || !r) __trap();
 }
 __device__ __forceinline__ void chain_wait(uint32_t bar, uint32_t parity, int tag) {
   for (uint32_t it = 0;; ++it) {
     if (mbar_try(bar, parity)) return;
-    if (it > (1u << 22)) chain_stuck(bar, parity, tag);
+    if (it > (1u << 20)) chain_stuck(bar, parity, tag, it);
   }
 }
 
@@ -328,7 +328,7 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
               for (uint32_t it = 0;; ++it) {
                 const uint32_t ok = mbar_try(sgb, sgp) & mbar_try(fullB + 8 * b_slot, b_phase) & mbar_try(fullA + 8 * sl, ph);
                 if (ok) break;
-                if (it > (1u << 22)) chain_stuck(fullA + 8 * sl, ph, 2 | (mbar_try(fullB + 8 * b_slot, b_phase) ? 0 : 16) | (t << 8));
+                if (it > (1u << 20)) chain_stuck(fullA + 8 * sl, ph, 2 | (mbar_try(fullB + 8 * b_slot, b_phase) ? 0 : 16) | (mbar_try(sgb, sgp) ? 0 : 32) | (t << 8), it);
               }
               CH_PROF_END(pw1);
             }
