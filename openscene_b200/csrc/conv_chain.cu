@@ -10,9 +10,8 @@
 //   warps 0-3   epilogue of both TMEM accumulator buffers: TMEM -> registers -> BN affine / residual / ReLU -> swizzled
 //               staging tile -> full-line coalesced stores (split rows, fp32 rows, or raw split-K partials)
 //   warp 4      weight tiles: one cp.async.bulk per stage from the tile-major, pre-swizzled packing (no tensor map)
-//   warps 5-8   tcgen05.mma issuers (one thread each), one per sub-tile of an item (up to four 128-row sub-tiles share every
-//               weight tile); a single thread can issue one MMA per ~90 cycles, the pipe needs 48 for M128 x N96 x K16
-//   warps 9-15  gathered A rows: cp.async 16 B x 8 lanes per 128-byte row line, hand-applied 128B swizzle, the kernel
+//   warps 5-6   tcgen05.mma issuers (one thread each): warp 5 owns sub-tile 0 of an item, warp 6 sub-tile 1; warp 5 owns TMEM
+//   warps 8-15  gathered A rows: cp.async 16 B x 8 lanes per 128-byte row line, hand-applied 128B swizzle, the kernel
 //               map read per offset straight from global memory, one offset ahead
 //
 // What changed against conv_tc.cu, and why (profiles/r01_ncu_full_conv_tc_96x96_k3_final.md, DESIGN.md "slot model"):
@@ -34,7 +33,7 @@
 
 namespace osb {
 
-constexpr int CH_THREADS = 512;                  // 16 warps: 4 epilogue, 1 weights, 4 MMA issuers, 7 gather
+constexpr int CH_THREADS = 384;                  // 12 warps (3 per scheduler -> 168 registers each): 4 epilogue, 1 weights, 2 MMA issuers, 5 gather
 constexpr int CH_M = 128;                        // rows per sub-tile (UMMA M)
 constexpr int CH_A_BYTES = CH_M * 128;           // one row slot: 128 rows x one 32-channel block
 constexpr int CH_STG_BYTES = 4 * 4096;           // epilogue staging: 4 warps x (32 rows x 128 B)
@@ -42,14 +41,13 @@ constexpr int CH_SS_FLOATS = 768;                // folded BN constants kept in 
 constexpr int CH_MAX_SA = 12, CH_MAX_SB = 4;
 // Warp roles.  Measured with per-role cycle counters (profiles/r02_chain_roles.md): every role is ONE warp walking a
 // dependent instruction chain, so its fixed cost per row slot (barrier wait, address set-up, arrival: 300-500 cycles) is
-// latency, not throughput.  Gather producers therefore own whole slots (warp w fills every CH_A_WARPS-th slot, 32 copy
+// latency, not throughput.  Gather producers therefore own whole slots (ring slot s is always filled by warp s mod CH_A_WARPS, 32 copy
 // instructions behind one wait / one arrival), the epilogue (idle 90 % of the time) gets four warps for both TMEM buffers.
-constexpr int CH_W_EPI = 0;                       // warps 0-3: epilogue (warp % 4 = TMEM lane quarter) of every sub-tile in turn
+constexpr int CH_W_EPI = 0;                       // warps 0-3: epilogue (warp % 4 = TMEM lane quarter), both accumulator buffers
 constexpr int CH_W_B = 4;                         // weight tiles
-constexpr int CH_W_MMA = 5;                       // warps 5-8: MMA issuers, one per sub-tile of an item; warp 5 owns the TMEM allocation
-constexpr int CH_MMA_WARPS = 4;
-constexpr int CH_W_A = 9;                         // warps 9-15: gathered rows, one whole 128-row slot at a time each
-constexpr int CH_A_WARPS = 7;
+constexpr int CH_W_MMA = 5;                       // warps 5, 6: MMA issuers; warp 5 owns the TMEM allocation
+constexpr int CH_W_A = 7;                         // warps 7-11: gathered rows, one whole 128-row slot at a time each
+constexpr int CH_A_WARPS = 5;
 constexpr int CH_DESC_WORDS = 48;                // sizeof(ConvDesc) / 4
 constexpr int CH_MAX_LAYERS = 16;                // layers per launch: the descriptors travel as kernel parameters (3 KB)
 
@@ -68,7 +66,7 @@ struct __align__(16) ConvDesc {
   int K, nb0, nb1;
   int cout, cout_pad, nt, n_ntiles;
   int relu, cmap_cout, nsplit, m_tiles;
-  int nsub_max;                    // sub-tiles per item that may share a weight tile: 4 when nt <= 128, else 2 (512 TMEM columns)
+  int nsub_max;                    // sub-tiles per item that may share a weight tile: 2 when nt <= 128, else 1
   int barrier_before;              // grid barrier before this layer (it reads what an earlier layer of the launch wrote)
   int stages_per_split;            // ceil(K * (nb0 + nb1) / nsplit)
   int pad[8];
@@ -203,7 +201,7 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
   uint8_t *aux = smem + (stg_u32 - base_u32) + CH_STG_BYTES;
   float *s_ss = reinterpret_cast<float *>(aux);                              // [scale x CH_SS_FLOATS | shift x CH_SS_FLOATS]
   uint64_t *bars = reinterpret_cast<uint64_t *>(s_ss + 2 * CH_SS_FLOATS);
-  uint32_t *s_misc = reinterpret_cast<uint32_t *>(bars + 44);                // [0] TMEM base
+  uint32_t *s_misc = reinterpret_cast<uint32_t *>(bars + 40);                // [0] TMEM base
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (flags & 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -211,14 +209,13 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
   long long pw0 = 0, pw1 = 0, pw2 = 0, pt = 0;     // cycles in this role's waits (up to three kinds) and in its loop
   if (dbg_clock && tid == 0) dbg_clock[blockIdx.x * 32 + 0] = clock64();
   uint32_t fullA = smem_u32(bars), emptyA = fullA + 12 * 8, fullB = fullA + 24 * 8, emptyB = fullA + 28 * 8;
-  uint32_t accFull = fullA + 32 * 8, accEmpty = fullA + 36 * 8, stageBar = fullA + 40 * 8;
-  CH_KEEP(fullA); CH_KEEP(emptyA); CH_KEEP(fullB); CH_KEEP(emptyB); CH_KEEP(accFull); CH_KEEP(accEmpty); CH_KEEP(stageBar);
+  uint32_t accFull = fullA + 32 * 8, accEmpty = fullA + 34 * 8;
+  CH_KEEP(fullA); CH_KEEP(emptyA); CH_KEEP(fullB); CH_KEEP(emptyB); CH_KEEP(accFull); CH_KEEP(accEmpty);
 
   if (tid == 0) {
-    for (int s = 0; s < sa; ++s) { mbar_init(fullA + 8 * s, 1); mbar_init(emptyA + 8 * s, 1); }    // fullA: one arrival by the slot's warp
-    for (int s = 0; s < sb; ++s) { mbar_init(fullB + 8 * s, 1); mbar_init(emptyB + 8 * s, CH_MMA_WARPS); }   // emptyB: one arrival per issuer
-    for (int b = 0; b < 4; ++b) { mbar_init(accFull + 8 * b, 1); mbar_init(accEmpty + 8 * b, 4); }   // per sub-tile accumulator
-    for (int b = 0; b < 2; ++b) mbar_init(stageBar + 8 * b, CH_MMA_WARPS);                          // issuer skew limiter
+    for (int s = 0; s < sa; ++s) { mbar_init(fullA + 8 * s, 32); mbar_init(emptyA + 8 * s, 1); }   // fullA: the 32 lanes of the slot's warp
+    for (int s = 0; s < sb; ++s) { mbar_init(fullB + 8 * s, 1); mbar_init(emptyB + 8 * s, 2); }   // emptyB: one arrival per issuer
+    for (int b = 0; b < 2; ++b) { mbar_init(accFull + 8 * b, 2); mbar_init(accEmpty + 8 * b, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == CH_W_MMA) {   // all 512 TMEM columns: two accumulator buffers of 256 columns (one CTA per SM, no contention)
@@ -236,9 +233,7 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
   if (dbg_clock && tid == 0) dbg_clock[blockIdx.x * 32 + 1] = clock64();
 
   // pipeline state of this thread's role; persists over items and layers
-  uint32_t a_slot = 0, a_phase = 0, b_slot = 0, b_phase = 0;
-  uint32_t n_stage = 0;                            // MMA issuers: stages gone through (skew limiter below)
-  uint32_t use_bits = 0;                           // parity of the uses of accumulator s (bit s): issuers track their own, the epilogue all four
+  uint32_t a_slot = 0, a_phase = 0, b_slot = 0, b_phase = 0, n_item = 0;
   uint32_t g_slot = 0;                             // gather producers: row slots the CTA has gone through before the current item
   uint32_t p_sl = warp >= CH_W_A ? (uint32_t)(warp - CH_W_A) : 0u, p_lapb = 0, p_par = 0;   // gather producers: my next ring slot, global index of slot 0 of its lap, lap parity
 
@@ -273,7 +268,7 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
 #define CH_FOR_ITEMS()                                                                                         \
     for (int64_t u = u_begin, _n; u < u_end; u += _n)                                                          \
       if (const int z = (int)(u / per_z), r_ = (int)(u - (int64_t)z * per_z), nti = r_ / d_m_tiles,            \
-          m = r_ - nti * d_m_tiles, nsub = (int)min((int64_t)min(d_nsub_max, d_m_tiles - m), u_end - u),        \
+          m = r_ - nti * d_m_tiles, nsub = (d_nsub_max == 2 && u + 1 < u_end && m + 1 < d_m_tiles) ? 2 : 1,    \
           t_begin = min(z * d_sps, T), t_end = min(t_begin + d_sps, T);                                        \
           (_n = nsub, true))
 
@@ -284,7 +279,7 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
       CH_FOR_ITEMS() {
         (void)m;
         for (int t = t_begin; t < t_end; ++t) {
-          { CH_PROF_BEGIN(); chain_wait(emptyB + 8 * b_slot, b_phase ^ 1, 5 | (t << 8)); CH_PROF_END(pw0); }
+          { CH_PROF_BEGIN(); mbar_wait_relaxed(emptyB + 8 * b_slot, b_phase ^ 1, 64); CH_PROF_END(pw0); }
           if (elect_one()) {
             const uint32_t fb = fullB + 8 * b_slot;
             if (flags & 0x200) {                      // tuning: no weight loads
@@ -298,76 +293,102 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
           if (++b_slot == (uint32_t)sb) { b_slot = 0; b_phase ^= 1; }
         }
       }
-    } else if (warp >= CH_W_MMA && warp < CH_W_MMA + CH_MMA_WARPS) {
-      // ============ MMA issuers: warp CH_W_MMA + i owns sub-tile i of every item ===============
-      // Measured (profiles/r02_chain_roles.md): one thread issues one tcgen05.mma per ~90 cycles and pays ~300 cycles of
-      // barrier probe / proxy fence / descriptor set-up / commit per row slot, i.e. ~830 cycles per slot against 288 cycles
-      // of tensor work (M128 x N96 x K16 x 6).  Only concurrent issue streams fill the pipe: up to four sub-tiles of an item
-      // are issued by four threads on disjoint accumulator columns, each in stage order (bit-reproducible accumulation).
+    } else if (warp == CH_W_MMA || warp == CH_W_MMA + 1) {
+      // ============ MMA issuers: warp CH_W_MMA owns sub-tile 0 of every item, the next warp sub-tile 1 ===============
+      // One issuing thread spends ~64 cycles per tcgen05.mma plus ~400 cycles of barrier-wait / fence / commit per row
+      // slot, more than the 288 cycles of tensor work a 96-channel slot carries; two issuers on disjoint accumulator
+      // columns restore the slack two co-resident CTAs used to give.  Each sub-tile's MMAs are issued by one thread, in
+      // stage order (bit-reproducible accumulation).
       const int mi = warp - CH_W_MMA;
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(d_nt >> 3) << 17) | ((uint32_t)(CH_M >> 4) << 24);
-      const uint32_t dcol = tmem_base + (uint32_t)mi * (d_nt > 128 ? 256u : 128u);
       CH_FOR_ITEMS() {
         (void)m; (void)nti;
+        const uint32_t buf = n_item & 1u;
         const bool mine = mi < nsub;
-        if (mine) {                                   // the epilogue drained my accumulator (previous use)
-          CH_PROF_BEGIN(); chain_wait(accEmpty + 8 * (uint32_t)mi, (use_bits & 1u) ^ 1u, 1); CH_PROF_END(pw2);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        }
-        for (int t = t_begin; t < t_end; ++t) {
-          // Skew limiter.  The row ring is SHARED by the issuers (slot s is read by different issuers in different laps) and
-          // an mbarrier only tells phase parity: an issuer more than one lap ahead of the slowest one would mistake "lap L-2
-          // filled" for "lap L filled".  The weight ring alone allows a skew of sb - 1 = 2 stages, a lap of the row ring can be
-          // as short as sa / nsub = 2.5 stages.  No issuer starts stage n before all have finished stage n - 2.
-          const uint32_t sgb = stageBar + 8 * (n_stage & 1u), sgp = ((n_stage >> 1) & 1u) ^ 1u;
+        // Both issuers follow the full protocol of every item, also the one without a sub-tile of its own (single-sub-tile
+        // items): its arrivals on emptyB / accFull may only happen in the phase they belong to, i.e. after the same waits.
+        { CH_PROF_BEGIN(); mbar_wait(accEmpty + 8 * buf, ((n_item >> 1) & 1u) ^ 1u); CH_PROF_END(pw2); }   // the epilogue drained this buffer
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t dcol = tmem_base + buf * 256u + (uint32_t)mi * 128u;
+        // two stages per iteration: the fixed cost of an iteration (waits, proxy fence, election, descriptor set-up) is a
+        // dependent chain of a few hundred cycles; 12 MMAs behind it instead of 6
+        for (int t = t_begin; t < t_end;) {
+          const int nst = min(2, t_end - t);
+          uint32_t sl[2], sph[2], bs[2], bph[2];
+          {
+            uint32_t as_ = a_slot + (uint32_t)mi, ap_ = a_phase, bs_ = b_slot, bp_ = b_phase;
+            if (as_ >= (uint32_t)sa) { as_ -= (uint32_t)sa; ap_ ^= 1u; }
+#pragma unroll
+            for (int jx = 0; jx < 2; ++jx) {
+              sl[jx] = as_; sph[jx] = ap_; bs[jx] = bs_; bph[jx] = bp_;
+              as_ += (uint32_t)nsub; if (as_ >= (uint32_t)sa) { as_ -= (uint32_t)sa; ap_ ^= 1u; }
+              if (++bs_ == (uint32_t)sb) { bs_ = 0; bp_ ^= 1u; }
+            }
+          }
           if (mine) {
-            uint32_t sl = a_slot + (uint32_t)mi, ph = a_phase;             // my row slot of this stage
-            if (sl >= (uint32_t)sa) { sl -= (uint32_t)sa; ph ^= 1u; }
-            {                                         // both barriers probed together (overlapping round trips)
+            {                                         // all barriers of the batch probed together (overlapping round trips)
               CH_PROF_BEGIN();
+              const bool two = nst == 2;
+              const uint32_t b1 = two ? bs[1] : bs[0], bp1 = two ? bph[1] : bph[0], a1 = two ? sl[1] : sl[0], ap1 = two ? sph[1] : sph[0];
               for (uint32_t it = 0;; ++it) {
-                const uint32_t ok = mbar_try(sgb, sgp) & mbar_try(fullB + 8 * b_slot, b_phase) & mbar_try(fullA + 8 * sl, ph);
+                const uint32_t ok = mbar_try(fullB + 8 * bs[0], bph[0]) & mbar_try(fullA + 8 * sl[0], sph[0]) &
+                                    mbar_try(fullB + 8 * b1, bp1) & mbar_try(fullA + 8 * a1, ap1);
                 if (ok) break;
-                if (it > (1u << 20)) chain_stuck(fullA + 8 * sl, ph, 2 | (mbar_try(fullB + 8 * b_slot, b_phase) ? 0 : 16) | (mbar_try(sgb, sgp) ? 0 : 32) | (t << 8), it);
+                if (it > (1u << 26)) __trap();
               }
               CH_PROF_END(pw1);
             }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) writes -> UMMA reads
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (flags & 0x4000) {                     // tuning: plain arrivals instead of tcgen05.commit (only without MMAs)
-              if (lane == 0) { mbar_arrive(emptyA + 8 * sl); mbar_arrive(emptyB + 8 * b_slot); }
-            } else if (elect_one()) {
-              const uint64_t db = umma_desc(b_ring_k + b_slot * (uint32_t)bslot);
-              const uint64_t da = umma_desc(a_ring_k + sl * (uint32_t)CH_A_BYTES);
-              // 128-byte line = [hi ch0-15 | hi ch16-31 | lo ch0-15 | lo ch16-31]; +2 per 32-byte K slice
+              if (lane == 0) {
 #pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                if (flags & 0x400) break;             // tuning: no MMAs
-                umma_bf16(dcol, da + 2 * h, db + 2 * h, idesc, (h == 0 && t == t_begin) ? 0u : 1u);   // hi * Whi
-                umma_bf16(dcol, da + 2 * h, db + 2 * h + 4, idesc, 1u);                                // hi * Wlo
-                umma_bf16(dcol, da + 2 * h + 4, db + 2 * h, idesc, 1u);                                // lo * Whi
+                for (int jx = 0; jx < 2; ++jx)
+                  if (jx < nst) { mbar_arrive(emptyA + 8 * sl[jx]); mbar_arrive(emptyB + 8 * bs[jx]); }
               }
-              umma_commit(emptyA + 8 * sl);                                 // row slot free when these MMAs retire
-              umma_commit(emptyB + 8 * b_slot);                             // weight slot: one arrival per issuer
+            } else if (elect_one()) {
+#pragma unroll
+              for (int jx = 0; jx < 2; ++jx) {
+                if (jx < nst) {
+                  const uint64_t db = umma_desc(b_ring_k + bs[jx] * (uint32_t)bslot);
+                  const uint64_t da = umma_desc(a_ring_k + sl[jx] * (uint32_t)CH_A_BYTES);
+                  // 128-byte line = [hi ch0-15 | hi ch16-31 | lo ch0-15 | lo ch16-31]; +2 per 32-byte K slice
+#pragma unroll
+                  for (int h = 0; h < 2; ++h) {
+                    if (flags & 0x400) break;         // tuning: no MMAs
+                    umma_bf16(dcol, da + 2 * h, db + 2 * h, idesc, (h == 0 && jx == 0 && t == t_begin) ? 0u : 1u);   // hi * Whi
+                    umma_bf16(dcol, da + 2 * h, db + 2 * h + 4, idesc, 1u);                                          // hi * Wlo
+                    umma_bf16(dcol, da + 2 * h + 4, db + 2 * h, idesc, 1u);                                          // lo * Whi
+                  }
+                  umma_commit(emptyA + 8 * sl[jx]);                         // row slot free when these MMAs retire
+                  umma_commit(emptyB + 8 * bs[jx]);                         // weight slot: one arrival per issuer
+                }
+              }
             }
           } else {
-            // No sub-tile of mine in this item: still one arrival per weight slot, and only in the phase it belongs to
-            // (the slot's full barrier of this stage has completed).
-            chain_wait(sgb, sgp, 7);
-            chain_wait(fullB + 8 * b_slot, b_phase, 3);
-            if (lane == 0) mbar_arrive(emptyB + 8 * b_slot);
+#pragma unroll
+            for (int jx = 0; jx < 2; ++jx) {
+              if (jx < nst) {
+                mbar_wait(fullB + 8 * bs[jx], bph[jx]);                     // stay in step with the slot's phase ...
+                if (lane == 0) mbar_arrive(emptyB + 8 * bs[jx]);            // ... nothing of mine reads this weight tile
+              }
+            }
           }
           __syncwarp();
-          if (lane == 0) mbar_arrive(sgb);            // this stage is behind me (its MMAs are issued)
-          ++n_stage;
-          a_slot += (uint32_t)nsub;
-          if (a_slot >= (uint32_t)sa) { a_slot -= (uint32_t)sa; a_phase ^= 1u; }
-          if (++b_slot == (uint32_t)sb) { b_slot = 0; b_phase ^= 1; }
+#pragma unroll
+          for (int jx = 0; jx < 2; ++jx) {
+            if (jx < nst) {
+              a_slot += (uint32_t)nsub;
+              if (a_slot >= (uint32_t)sa) { a_slot -= (uint32_t)sa; a_phase ^= 1u; }
+              if (++b_slot == (uint32_t)sb) { b_slot = 0; b_phase ^= 1; }
+            }
+          }
+          t += nst;
         }
-        if (mine) {
-          if (elect_one()) umma_commit(accFull + 8 * (uint32_t)mi);
-          __syncwarp();
-          use_bits ^= 1u;
-        }
+        if (mine) { if (elect_one()) umma_commit(accFull + 8 * buf); }
+        else if (lane == 0) mbar_arrive(accFull + 8 * buf);
+        __syncwarp();
+        ++n_item;
       }
     } else if (warp >= CH_W_A) {
       // ================= gathered A rows: warp w fills every CH_A_WARPS-th row slot, all 128 rows of it ====================
@@ -443,15 +464,7 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
               }
             }
           }
-          // Completion on the WRITER side (the documented cross-proxy pattern): wait for my copies, make them visible to the
-          // async proxy the tensor core reads shared memory through, then one arrival per warp.  The self-tracking
-          // `cp.async.mbarrier.arrive.noinc` + a proxy fence on the consumer side (first-generation kernel) let the slot that
-          // is multiplied right after it lands be read stale now and then (profiles/r02_chain_roles.md, item 5).
-          asm volatile("cp.async.commit_group;" ::: "memory");
-          asm volatile("cp.async.wait_group 0;" ::: "memory");
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) mbar_arrive(fullA + 8 * sl);
+          cp_async_arrive_noinc(fullA + 8 * sl);      // 32 self-tracking arrivals, fired by the copy engine
         }
         g_slot = g_end;
       }
@@ -470,11 +483,11 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
       const int32_t *d_row_map = s_desc->out_row_map, *d_cmap = s_desc->cmap;
       auto lds128 = [](uint32_t a) { uint4 v; asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; };
       auto sts128 = [](uint32_t a, uint4 v) { asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); };
-      const uint32_t sub_cols = d_nt > 128 ? 256u : 128u;
       CH_FOR_ITEMS() {
+        const uint32_t buf = n_item & 1u;
+        { CH_PROF_BEGIN(); mbar_wait_relaxed(accFull + 8 * buf, (n_item >> 1) & 1u, 128); CH_PROF_END(pw0); }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int s = 0; s < nsub; ++s) {
-          { CH_PROF_BEGIN(); chain_wait(accFull + 8 * (uint32_t)s, (use_bits >> s) & 1u, 6 | (s << 8)); CH_PROF_END(pw0); }
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const int64_t wrow0 = (int64_t)(m + s) * CH_M + q * 32;        // first global row of this warp
           const int64_t o = wrow0 + lane;
           int32_t my_orow = (int32_t)min(o, d_n_out - 1);
@@ -500,7 +513,7 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
             float y[32];
             {
               uint32_t v0[16], v1[16];
-              const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)s * sub_cols + cbo * 32;
+              const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256u + (uint32_t)s * 128u + cbo * 32;
               tmem_ld16(taddr, v0);
               tmem_ld16(taddr + 16, v1);
               asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -579,12 +592,12 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
               __syncwarp();
             }
           }
-          // this warp's TMEM reads of the sub-tile are complete (tcgen05.wait::ld above): hand it back to its issuer
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) mbar_arrive(accEmpty + 8 * (uint32_t)s);
-          use_bits ^= 1u << s;
         }
+        // this warp's TMEM reads of the buffer are complete (tcgen05.wait::ld above): hand it back to the MMA warps
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(accEmpty + 8 * buf);
+        ++n_item;
       }
     }
 #undef CH_FOR_ITEMS
@@ -709,12 +722,12 @@ static int chain_nsplit(int64_t n_out, int K, int cin, int cout, int grid_ctas, 
 }
 
 static int g_chain_force_split = 0;      // tuning: > 0 forces the split factor of every layer (1 disables splitting)
-static int g_chain_nsub = 4;             // tuning: most sub-tiles per item (1 = never share a weight tile)
+static int g_chain_nsub = 2;             // tuning: 1 = never pair sub-tiles
 static int g_chain_grid = 0;             // tuning: CTAs per launch (0 = one per SM)
 static int g_chain_sa = 0, g_chain_sb = 0;   // tuning: ring depths (0 = as many row slots as fit / 3 or 2 weight slots)
 static long long *g_chain_dbg_clock = nullptr;
 static int g_chain_dbg_skip = 0;         // tuning: bit0 no row copies, bit1 no weight loads, bit2 no MMAs, bit3 no stores,
-                                         // bit5 no tcgen05 fence, bit6 plain arrivals for commits, bit7 no turn-taking between the issuers
+                                         // bit5 no tcgen05 fence, bit6 plain arrivals for commits, bit8 legacy (consumer-side) completion
 
 int osb_tuning_set(const char *name, int64_t value) {
   const std::string n(name ? name : "");
@@ -768,7 +781,7 @@ int osb_conv_desc_fill(void *desc_host, const void *src0, int32_t c0, const void
   d.out_row_map = out_row_map; d.cmap = cmap; d.n_out = n_out; d.K = K; d.nb0 = c0 / 32; d.nb1 = c1 / 32;
   d.cout = cout; d.cout_pad = chain_cout_pad(cout); d.nt = chain_nt(cout); d.n_ntiles = d.cout_pad / d.nt;
   d.relu = relu; d.cmap_cout = cmap_cout; d.m_tiles = (int)ceil_div(n_out, CH_M);
-  d.nsub_max = std::max(1, std::min(g_chain_nsub, d.nt <= 128 ? 4 : 2));
+  d.nsub_max = (d.nt <= 128 && g_chain_nsub >= 2) ? 2 : 1;
   d.barrier_before = barrier_before ? 1 : 0;
   d.nsplit = cmap ? 1 : chain_nsplit(n_out, K, cin, cout, osb_conv_chain_grid(), g_chain_force_split);
   const int T = K * (cin / 32);
@@ -810,7 +823,7 @@ int osb_conv_chain_launch(const void *descs_host, int32_t n_layers, void *grid_b
     }
     OSB_CHECK(!need_bar || grid_barrier_dev != nullptr, "osb_conv_chain_launch: this chain needs the grid-barrier words");
     const int bslot = nt_max * 128;
-    const int fixed = 1024 + CH_STG_BYTES + 2 * CH_SS_FLOATS * 4 + 44 * 8 + 64;   // alignment slack, staging, BN constants, barriers
+    const int fixed = 1024 + CH_STG_BYTES + 2 * CH_SS_FLOATS * 4 + 40 * 8 + 64;   // alignment slack, staging, BN constants, barriers
     int sb = g_chain_sb > 0 ? g_chain_sb : (bslot >= 32768 ? 2 : 3);
     sb = std::min(sb, CH_MAX_SB);
     int sa = (227 * 1024 - fixed - sb * bslot) / CH_A_BYTES;

@@ -42,8 +42,7 @@ print(f'# {workload} n={n} {cin}->{cout} k={ks}')
 print(f'legacy k_conv_tc                         {timed(lambda: tc.conv_tc(x, cin, None, 0, nbr, n, ks ** 3, wp, cout)):8.1f} us')
 SETS = [
     ('chain default (noinc arrivals, consumer-side fence)', {}),
-    ('nsub=2', {'chain_nsub': 2}),
-    ('nsub=3', {'chain_nsub': 3}),
+
     ('nsub=1', {'chain_nsub': 1}),
     ('no A,B,MMA (0x7)', {'chain_dbg_skip': 0x7}),
     ('no A,B (0x3)', {'chain_dbg_skip': 0x3}),
@@ -56,7 +55,7 @@ SETS = [
     ('end', {}),
 ]
 for name, knobs in SETS[:-1]:
-    for k_, v_ in (('chain_dbg_skip', 0), ('chain_nsub', 4), ('chain_sa', 0)):
+    for k_, v_ in (('chain_dbg_skip', 0), ('chain_nsub', 2), ('chain_sa', 0)):
         tc.tuning_set(k_, v_)
     for k_, v_ in knobs.items():
         tc.tuning_set(k_, v_)

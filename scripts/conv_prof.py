@@ -39,7 +39,7 @@ print(f'# {workload} n={n} {cin}->{cout} k={ks} knobs={knobs}: {a.elapsed_time(b
 tot = (d[:, 2] - d[:, 0])
 print(f'CTA cycles: mean {tot.mean():.0f} max {tot.max():.0f}; set-up {(d[:, 1] - d[:, 0]).mean():.0f}')
 rows = [('B producer', 4, ('wait emptyB', '-', '-')), ('issuer 0', 8, ('wait fullB', 'wait fullA', 'wait accEmpty')),
-        ('issuer 1 (of 4)', 12, ('wait fullB', 'wait fullA', 'wait accEmpty')), ('gather producer (1 of 7 warps)', 16, ('wait emptyA', 'index loads land', '-')),
+        ('issuer 1', 12, ('wait fullB', 'wait fullA', 'wait accEmpty')), ('gather producer (1 of 5 warps)', 16, ('wait emptyA', 'index loads land', '-')),
         ('epilogue (1 of 4 warps)', 20, ('wait accFull', '-', '-'))]
 for name, base, labels in rows:
     w0, w1, w2, t = (d[:, base + i].mean().item() for i in range(4))
