@@ -284,6 +284,7 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
     // so that the two pipelines do not reach their item boundaries (accumulator hand-over to the epilogue) together.
     const int64_t u_mid = npipe == 2 ? u_begin + (u_end - u_begin + 1) / 2 : u_end;
     const int64_t pu_begin = P ? u_mid : u_begin, pu_end = P ? u_end : u_mid;
+    const bool stagger = !(flags & 0x20000);           // tuning bit 9: no staggered start
 
     // item = 1 or 2 consecutive units (same split, same N tile, adjacent row tiles) sharing every weight tile
 #define CH_ITEM_AT(u_, ub_, ue_, stag_)                                                                         \
@@ -293,7 +294,7 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
           t_begin = min(z * d_sps, T), t_end = min(t_begin + d_sps, T)
 #define CH_FOR_ITEMS()                                                                                          \
     for (int64_t u = pu_begin, _n; u < pu_end; u += _n)                                                         \
-      if (CH_ITEM_AT(u, pu_begin, pu_end, P == 1); (_n = nsub, true))
+      if (CH_ITEM_AT(u, pu_begin, pu_end, P == 1 && stagger); (_n = nsub, true))
 
     const long long _role_t0 = prof ? clock64() : 0;
     if (warp == CH_W_B || warp == CH_W_B + 1) {
@@ -527,7 +528,7 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
         { CH_PROF_BEGIN(); mbar_wait_relaxed(eFull, (ep ? e_item1 : e_item0) & 1u, 128); CH_PROF_END(pw0); }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int64_t eu = ep ? eu1 : eu0;
-        CH_ITEM_AT(eu, ep ? u_mid : u_begin, ep ? u_end : u_mid, ep == 1);
+        CH_ITEM_AT(eu, ep ? u_mid : u_begin, ep ? u_end : u_mid, ep == 1 && stagger);
         (void)t_begin; (void)t_end;
         for (int s = 0; s < nsub; ++s) {
           const int64_t wrow0 = (int64_t)(m + s) * CH_M + q * 32;        // first global row of this warp

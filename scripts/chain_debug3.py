@@ -12,6 +12,7 @@ from openscene_b200.coords import CoordinateManager  # noqa: E402
 
 grid, cin, cout, ks = (int(v) for v in sys.argv[1:5])
 runs = int(sys.argv[5]) if len(sys.argv) > 5 else 8
+knobs = dict(kv.split('=') for kv in sys.argv[6:])
 dev = torch.device('cuda:0')
 c = torch.from_numpy(synth.scene('tiny')).to(dev)
 cm = CoordinateManager(c)
@@ -22,6 +23,8 @@ x = torch.randn(n, cin, device=dev, generator=g)
 w = torch.randn(ks ** 3, cin, cout, device=dev, generator=g) * 0.05
 xs, wt = tc.to_split(x), tc.pack_weight_tiles(w)
 tc.tuning_set('chain_grid', grid)
+for k_, v_ in knobs.items():
+    tc.tuning_set(k_, int(v_, 0))
 ref = torch.zeros(n, cout, device=dev, dtype=torch.float64)
 for k in range(ks ** 3):
     o = (nbr[k] >= 0).nonzero()[:, 0]
