@@ -875,7 +875,12 @@ int osb_conv_chain_launch(const void *descs_host, int32_t n_layers, void *grid_b
     if (g_chain_sa > 0) sa = std::min(sa, g_chain_sa);
     sa = std::min(sa, npipe * CH_MAX_SA);
     OSB_CHECK(sa >= 2 * npipe, "osb_conv_chain_launch: shared memory does not hold two row slots per pipeline");
-    const int sa0 = npipe == 2 ? (sa + 1) / 2 : sa, sa1 = sa - sa0;
+    // Every ring gets an EVEN number of row slots: with two sub-tiles per stage a slot (and its two barriers) then always belongs to
+    // the same issuer.  With an odd ring the slots alternate between the two issuers from lap to lap; that variant produced stale
+    // rows on hardware in pipeline 1 (profiles/r02_chain_roles.md), as did the four-issuer kernel with a seven-slot ring.
+    int sa0 = npipe == 2 ? (sa + 1) / 2 : sa, sa1 = sa - sa0;
+    if (!(g_chain_dbg_skip & 0x400)) { sa0 &= ~1; sa1 &= ~1; }              // tuning bit 10: allow odd rings
+    sa = sa0 + sa1;
     const size_t smem_bytes = (size_t)sa * CH_A_BYTES + (size_t)npipe * sb * bslot + fixed;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

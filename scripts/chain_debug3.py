@@ -42,7 +42,7 @@ for rep in range(runs):
     err = ((o.double() - ref).norm(dim=1) / (ref.norm(dim=1) + 1e-9))
     bad = (err > 1e-4).nonzero()[:, 0]
     diff0 = (o != outs[0]).any(dim=1).nonzero()[:, 0]
-    print(f'run {rep}{" scattered" if scat else ""}: max rel err {float(err.max()):.3e}, rows off vs fp64 {len(bad)} tiles {sorted(set((bad // 128).tolist()))[:12]}; '
+    print(f'run: max rel err {float(err.max()):.3e}, rows off vs fp64 {len(bad)} tiles {sorted(set((bad // 128).tolist()))[:12]}; '
           f'rows differing from run 0: {len(diff0)} tiles {sorted(set((diff0 // 128).tolist()))[:12]}')
     if len(diff0):
         r = int(diff0[0])
