@@ -12,7 +12,7 @@
 //   TWO independent pipelines (P = 0, 1), each with its own rings, barriers, accumulator columns and half of the CTA's units:
 //   warp 4+P     weight tiles: one cp.async.bulk per stage from the tile-major, pre-swizzled packing (no tensor map)
 //   warps 6+2P.. two tcgen05.mma issuers (one thread each): sub-tile 0 and sub-tile 1 of the pipeline's current item
-//   warps 10+3P..three gather warps: cp.async 16 B x 8 lanes per 128-byte row line, hand-applied 128B swizzle, a whole
+//   warps 10+4P..four gather warps: cp.async 16 B x 8 lanes per 128-byte row line, hand-applied 128B swizzle, a whole
 //                128-row slot per warp, the kernel map read straight from global memory one slot ahead
 // Why two pipelines: one thread issues a tcgen05.mma every ~87 cycles (M128 x N96 x K16 needs 48 of the pipe), and a role
 // is a dependent instruction chain; the tensor pipe fills only with several issue streams in flight.  Four issuers on
@@ -38,7 +38,7 @@
 
 namespace osb {
 
-constexpr int CH_THREADS = 512;                  // 16 warps (128 registers each): 4 epilogue + 2 x (1 weights, 2 MMA issuers, 3 gather)
+constexpr int CH_THREADS = 576;                  // 18 warps (96 registers each): 4 epilogue + 2 x (1 weights, 2 MMA issuers, 4 gather)
 constexpr int CH_M = 128;                        // rows per sub-tile (UMMA M)
 constexpr int CH_A_BYTES = CH_M * 128;           // one row slot: 128 rows x one 32-channel block
 constexpr int CH_STG_BYTES = 4 * 4096;           // epilogue staging: 4 warps x (32 rows x 128 B)
@@ -51,8 +51,8 @@ constexpr int CH_MAX_SA = 8, CH_MAX_SB = 4;     // per pipeline
 constexpr int CH_W_EPI = 0;                       // warps 0-3: epilogue (warp % 4 = TMEM lane quarter), both pipelines
 constexpr int CH_W_B = 4;                         // warps 4, 5: weight tiles of pipeline 0, 1
 constexpr int CH_W_MMA = 6;                       // warps 6, 7: MMA issuers of pipeline 0; 8, 9: pipeline 1; warp 6 owns the TMEM allocation
-constexpr int CH_W_A = 10;                        // warps 10-12: gathered rows of pipeline 0; 13-15: pipeline 1
-constexpr int CH_A_WARPS = 3;                     // per pipeline
+constexpr int CH_W_A = 10;                        // warps 10-13: gathered rows of pipeline 0; 14-17: pipeline 1
+constexpr int CH_A_WARPS = 4;                     // per pipeline: with a four-slot ring every warp owns exactly one slot
 constexpr int CH_BARS = 32;                       // mbarriers per pipeline: fullA[8] emptyA[8] fullB[4] emptyB[4] accFull accEmpty
 constexpr int CH_DESC_WORDS = 48;                // sizeof(ConvDesc) / 4
 constexpr int CH_MAX_LAYERS = 16;                // layers per launch: the descriptors travel as kernel parameters (3 KB)
@@ -190,6 +190,7 @@ __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void *src, 
 }
 
 // ------------------------------------------------------------------------------------ the kernel
+template <bool PROF>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gbar, int sa0, int sa1, int sb, int bslot, int flags,
              long long *dbg_clock) {
@@ -215,9 +216,9 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
   uint32_t *s_misc = reinterpret_cast<uint32_t *>(bars + 2 * CH_BARS);       // [0] TMEM base
 
   if (flags & 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  const bool prof = dbg_clock != nullptr;
+  constexpr bool prof = PROF;                      // per-role cycle accounting: a separate instantiation (it costs ~10 registers)
   long long pw0 = 0, pw1 = 0, pw2 = 0, pt = 0;     // cycles in this role's waits (up to three kinds) and in its loop
-  if (dbg_clock && tid == 0) dbg_clock[blockIdx.x * 80 + 64] = clock64();
+  if (prof && tid == 0) dbg_clock[blockIdx.x * 96 + 80] = clock64();
   const uint32_t bars0 = smem_u32(bars);
   uint32_t fullA = bars0 + (uint32_t)P * (CH_BARS * 8), emptyA = fullA + 8 * 8, fullB = fullA + 16 * 8, emptyB = fullA + 20 * 8;
   uint32_t accFull = fullA + 24 * 8, accEmpty = fullA + 25 * 8;
@@ -245,7 +246,7 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
   // Everything above touched no data of an earlier kernel in the stream; from here on we read activations.
   if (flags & 1) asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t tmem_base = s_misc[0];
-  if (dbg_clock && tid == 0) dbg_clock[blockIdx.x * 80 + 65] = clock64();
+  if (prof && tid == 0) dbg_clock[blockIdx.x * 96 + 81] = clock64();
 
   // pipeline state of this thread's role; persists over items and layers
   uint32_t a_slot = 0, a_phase = 0, b_slot = 0, b_phase = 0, n_item = 0;
@@ -259,7 +260,7 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
     const ConvDesc *s_desc = &args.d[L];               // parameter space: uniform loads
     const int d_K = s_desc->K, d_nb0 = s_desc->nb0, d_nb1 = s_desc->nb1, d_nt = s_desc->nt, d_n_ntiles = s_desc->n_ntiles;
     const int d_m_tiles = s_desc->m_tiles, d_nsplit = s_desc->nsplit, d_nsub_max = s_desc->nsub_max, d_sps = s_desc->stages_per_split;
-    const int64_t d_n_out = s_desc->n_out;
+    const int d_n_out = (int)s_desc->n_out;                 // < 2^31 (checked by osb_conv_desc_fill)
     {                                                  // folded BN constants of the layer -> shared memory
       const int nss = s_desc->cmap ? s_desc->cmap_cout : s_desc->cout;
       const float *sc = s_desc->scale, *sh = s_desc->shift;
@@ -276,24 +277,24 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
 
     const int nb = d_nb0 + d_nb1;
     const int T = d_K * nb;                                            // stages of one full (offset, channel block) sweep
-    const int64_t U = (int64_t)d_m_tiles * d_n_ntiles * d_nsplit;      // work units of the layer
-    const int64_t u_begin = U * blockIdx.x / gridDim.x, u_end = U * (blockIdx.x + 1) / gridDim.x;
+    const int U = d_m_tiles * d_n_ntiles * d_nsplit;                   // work units of the layer (< 2^31 / grid: checked on the host)
+    const int u_begin = (int)((int64_t)U * blockIdx.x / gridDim.x), u_end = (int)((int64_t)U * (blockIdx.x + 1) / gridDim.x);
     const int per_z = d_m_tiles * d_n_ntiles;
     const uint32_t b_bytes = (uint32_t)d_nt * 128u;
     // The CTA's units are halved between the pipelines (contiguous ranges).  Pipeline 1 starts with a single-sub-tile item
     // so that the two pipelines do not reach their item boundaries (accumulator hand-over to the epilogue) together.
-    const int64_t u_mid = npipe == 2 ? u_begin + (u_end - u_begin + 1) / 2 : u_end;
-    const int64_t pu_begin = P ? u_mid : u_begin, pu_end = P ? u_end : u_mid;
+    const int u_mid = npipe == 2 ? u_begin + (u_end - u_begin + 1) / 2 : u_end;
+    const int pu_begin = P ? u_mid : u_begin, pu_end = P ? u_end : u_mid;
     const bool stagger = !(flags & 0x20000);           // tuning bit 9: no staggered start
 
     // item = 1 or 2 consecutive units (same split, same N tile, adjacent row tiles) sharing every weight tile
 #define CH_ITEM_AT(u_, ub_, ue_, stag_)                                                                         \
-      const int z = (int)((u_) / per_z), r_ = (int)((u_) - (int64_t)z * per_z), nti = r_ / d_m_tiles,           \
+      const int z = (u_) / per_z, r_ = (u_) - z * per_z, nti = r_ / d_m_tiles,           \
           m = r_ - nti * d_m_tiles,                                                                             \
           nsub = (d_nsub_max == 2 && (u_) + 1 < (ue_) && m + 1 < d_m_tiles && !((stag_) && (u_) == (ub_))) ? 2 : 1,   \
           t_begin = min(z * d_sps, T), t_end = min(t_begin + d_sps, T)
 #define CH_FOR_ITEMS()                                                                                          \
-    for (int64_t u = pu_begin, _n; u < pu_end; u += _n)                                                         \
+    for (int u = pu_begin, _n; u < pu_end; u += _n)                                                             \
       if (CH_ITEM_AT(u, pu_begin, pu_end, P == 1 && stagger); (_n = nsub, true))
 
     const long long _role_t0 = prof ? clock64() : 0;
@@ -441,7 +442,7 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
           const int32_t *nk = nbr ? nbr + (int64_t)k_ * d_n_out : nullptr;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const int64_t o = (int64_t)(m + s_) * CH_M + 32 * i + lane;
+            const int o = (m + s_) * CH_M + 32 * i + lane;
             r[i] = (o < d_n_out) ? (nk ? __ldg(nk + o) : (int32_t)o) : -1;
           }
         };
@@ -507,7 +508,7 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
       auto lds128 = [](uint32_t a) { uint4 v; asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; };
       auto sts128 = [](uint32_t a, uint4 v) { asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); };
       // Both pipelines' items, each pipeline's in its own order, whichever accumulator is complete first.
-      int64_t eu0 = u_begin, eu1 = u_mid;
+      int eu0 = u_begin, eu1 = u_mid;
       while (eu0 < u_mid || eu1 < u_end) {
         int ep;
         if (eu1 >= u_end) ep = 0;
@@ -527,13 +528,13 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
         const uint32_t eFull = bars0 + (uint32_t)ep * (CH_BARS * 8) + 24 * 8, eEmpty = eFull + 8;
         { CH_PROF_BEGIN(); mbar_wait_relaxed(eFull, (ep ? e_item1 : e_item0) & 1u, 128); CH_PROF_END(pw0); }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int64_t eu = ep ? eu1 : eu0;
+        const int eu = ep ? eu1 : eu0;
         CH_ITEM_AT(eu, ep ? u_mid : u_begin, ep ? u_end : u_mid, ep == 1 && stagger);
         (void)t_begin; (void)t_end;
         for (int s = 0; s < nsub; ++s) {
           const int64_t wrow0 = (int64_t)(m + s) * CH_M + q * 32;        // first global row of this warp
           const int64_t o = wrow0 + lane;
-          int32_t my_orow = (int32_t)min(o, d_n_out - 1);
+          int32_t my_orow = (int32_t)min(o, (int64_t)d_n_out - 1);
           if (d_row_map && o < d_n_out) my_orow = __ldg(d_row_map + o);
           // staged tile (32 rows x 128 B, swizzled) -> global, 4 full lines per instruction
           auto flush_tile = [&](uint8_t *base, int64_t row_bytes, int64_t col_byte, bool mapped) {
@@ -695,9 +696,9 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
     }
   }
 
-  if (dbg_clock && tid == 0) dbg_clock[blockIdx.x * 80 + 66] = clock64();
-  if (dbg_clock && lane == 0) {      // per warp: [wait kind 0, wait kind 1, wait kind 2, role loop total]; CTA time stamps at 64..66
-    long long *o = dbg_clock + blockIdx.x * 80 + warp * 4;
+  if (prof && tid == 0) dbg_clock[blockIdx.x * 96 + 82] = clock64();
+  if (prof && lane == 0) {      // per warp: [wait kind 0, wait kind 1, wait kind 2, role loop total]; CTA time stamps at 80..82
+    long long *o = dbg_clock + blockIdx.x * 96 + warp * 4;
     o[0] = pw0; o[1] = pw1; o[2] = pw2; o[3] = pt;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -851,7 +852,8 @@ int osb_conv_chain_launch(const void *descs_host, int32_t n_layers, void *grid_b
     OSB_CHECK(i == 0 || h[i].barrier_before || h[i].nsplit == 1 || h[i - 1].nsplit == 1 || h[i].partial != h[i - 1].partial,
               "osb_conv_chain_launch: layers %d and %d share a split workspace without a barrier between them", i - 1, i);
   }
-  OSB_SMEM_ATTR_ONCE(k_conv_chain, 227 * 1024);
+  OSB_SMEM_ATTR_ONCE(k_conv_chain<false>, 227 * 1024);
+  if (g_chain_dbg_clock) { OSB_SMEM_ATTR_ONCE(k_conv_chain<true>, 227 * 1024); }
   const int grid = osb_conv_chain_grid();
   // the layer descriptors travel as kernel parameters: at most CH_MAX_LAYERS per launch, longer lists in several launches
   // (a launch boundary orders everything, so the first layer of a later launch needs no grid barrier)
@@ -878,8 +880,13 @@ int osb_conv_chain_launch(const void *descs_host, int32_t n_layers, void *grid_b
     // Every ring gets an EVEN number of row slots: with two sub-tiles per stage a slot (and its two barriers) then always belongs to
     // the same issuer.  With an odd ring the slots alternate between the two issuers from lap to lap; that variant produced stale
     // rows on hardware in pipeline 1 (profiles/r02_chain_roles.md), as did the four-issuer kernel with a seven-slot ring.
+    // (tuning bit 10 of chain_dbg_skip lifts the rule.)  Four gather warps per pipeline: rings of 8, 4 or 2 slots keep their load even.
     int sa0 = npipe == 2 ? (sa + 1) / 2 : sa, sa1 = sa - sa0;
-    if (!(g_chain_dbg_skip & 0x400)) { sa0 &= ~1; sa1 &= ~1; }              // tuning bit 10: allow odd rings
+    if (!(g_chain_dbg_skip & 0x400)) {
+      const int per = sa / npipe;
+      sa0 = per >= 8 ? 8 : per >= 4 ? 4 : 2;
+      sa1 = npipe == 2 ? sa0 : 0;
+    }
     sa = sa0 + sa1;
     const size_t smem_bytes = (size_t)sa * CH_A_BYTES + (size_t)npipe * sb * bslot + fixed;
     cudaLaunchAttribute attr[1];
@@ -888,8 +895,12 @@ int osb_conv_chain_launch(const void *descs_host, int32_t n_layers, void *grid_b
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(CH_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
     cfg.attrs = attr; cfg.numAttrs = (flags & 1) ? 1 : 0;
-    OSB_CUDA(cudaLaunchKernelEx(&cfg, k_conv_chain, args, (int)cnt, (unsigned *)grid_barrier_dev, sa0, sa1, sb, bslot,
-                                (int)((flags & 1) | (g_chain_dbg_skip << 8)), g_chain_dbg_clock));
+    const int kflags = (int)((flags & 1) | (g_chain_dbg_skip << 8));
+    if (g_chain_dbg_clock) {
+      OSB_CUDA(cudaLaunchKernelEx(&cfg, k_conv_chain<true>, args, (int)cnt, (unsigned *)grid_barrier_dev, sa0, sa1, sb, bslot, kflags, g_chain_dbg_clock));
+    } else {
+      OSB_CUDA(cudaLaunchKernelEx(&cfg, k_conv_chain<false>, args, (int)cnt, (unsigned *)grid_barrier_dev, sa0, sa1, sb, bslot, kflags, (long long *)nullptr));
+    }
     OSB_LAUNCH_CHECK();
   }
   return 0;
