@@ -7,17 +7,12 @@
 // one split of the (offset, channel-block) stage sequence) and walks it with warp-specialised roles that never leave
 // their loops between units:
 //
-//   warps 0-3    epilogue of both pipelines' TMEM accumulators: TMEM -> registers -> BN affine / residual / ReLU ->
-//                swizzled staging tile -> full-line coalesced stores (split rows, fp32 rows, or raw split-K partials)
-//   TWO independent pipelines (P = 0, 1), each with its own rings, barriers, accumulator columns and half of the CTA's units:
-//   warp 4+P     weight tiles: one cp.async.bulk per stage from the tile-major, pre-swizzled packing (no tensor map)
-//   warps 6+2P.. two tcgen05.mma issuers (one thread each): sub-tile 0 and sub-tile 1 of the pipeline's current item
-//   warps 10+4P..four gather warps: cp.async 16 B x 8 lanes per 128-byte row line, hand-applied 128B swizzle, a whole
-//                128-row slot per warp, the kernel map read straight from global memory one slot ahead
-// Why two pipelines: one thread issues a tcgen05.mma every ~87 cycles (M128 x N96 x K16 needs 48 of the pipe), and a role
-// is a dependent instruction chain; the tensor pipe fills only with several issue streams in flight.  Four issuers on
-// ONE shared row ring could not be made to work on hardware (profiles/r02_chain_roles.md); two copies of the proven
-// two-issuer protocol share nothing but the epilogue warps.
+//   warps 0-3   epilogue of both TMEM accumulator buffers: TMEM -> registers -> BN affine / residual / ReLU -> swizzled
+//               staging tile -> full-line coalesced stores (split rows, fp32 rows, or raw split-K partials)
+//   warp 4      weight tiles: one cp.async.bulk per stage from the tile-major, pre-swizzled packing (no tensor map)
+//   warps 5-6   tcgen05.mma issuers (one thread each): warp 5 owns sub-tile 0 of an item, warp 6 sub-tile 1; warp 5 owns TMEM
+//   warps 8-15  gathered A rows: cp.async 16 B x 8 lanes per 128-byte row line, hand-applied 128B swizzle, the kernel
+//               map read per offset straight from global memory, one offset ahead
 //
 // What changed against conv_tc.cu, and why (profiles/r01_ncu_full_conv_tc_96x96_k3_final.md, DESIGN.md "slot model"):
 //   * separate rings for gathered rows and weight tiles; the whole SM's shared memory belongs to one CTA: 9-10 row
@@ -38,22 +33,21 @@
 
 namespace osb {
 
-constexpr int CH_THREADS = 576;                  // 18 warps (96 registers each): 4 epilogue + 2 x (1 weights, 2 MMA issuers, 4 gather)
+constexpr int CH_THREADS = 384;                  // 12 warps (3 per scheduler -> 168 registers each): 4 epilogue, 1 weights, 2 MMA issuers, 5 gather
 constexpr int CH_M = 128;                        // rows per sub-tile (UMMA M)
 constexpr int CH_A_BYTES = CH_M * 128;           // one row slot: 128 rows x one 32-channel block
 constexpr int CH_STG_BYTES = 4 * 4096;           // epilogue staging: 4 warps x (32 rows x 128 B)
 constexpr int CH_SS_FLOATS = 768;                // folded BN constants kept in shared memory per layer (scale | shift)
-constexpr int CH_MAX_SA = 8, CH_MAX_SB = 4;     // per pipeline
+constexpr int CH_MAX_SA = 12, CH_MAX_SB = 4;
 // Warp roles.  Measured with per-role cycle counters (profiles/r02_chain_roles.md): every role is ONE warp walking a
 // dependent instruction chain, so its fixed cost per row slot (barrier wait, address set-up, arrival: 300-500 cycles) is
 // latency, not throughput.  Gather producers therefore own whole slots (ring slot s is always filled by warp s mod CH_A_WARPS, 32 copy
 // instructions behind one wait / one arrival), the epilogue (idle 90 % of the time) gets four warps for both TMEM buffers.
-constexpr int CH_W_EPI = 0;                       // warps 0-3: epilogue (warp % 4 = TMEM lane quarter), both pipelines
-constexpr int CH_W_B = 4;                         // warps 4, 5: weight tiles of pipeline 0, 1
-constexpr int CH_W_MMA = 6;                       // warps 6, 7: MMA issuers of pipeline 0; 8, 9: pipeline 1; warp 6 owns the TMEM allocation
-constexpr int CH_W_A = 10;                        // warps 10-13: gathered rows of pipeline 0; 14-17: pipeline 1
-constexpr int CH_A_WARPS = 4;                     // per pipeline: with a four-slot ring every warp owns exactly one slot
-constexpr int CH_BARS = 32;                       // mbarriers per pipeline: fullA[8] emptyA[8] fullB[4] emptyB[4] accFull accEmpty
+constexpr int CH_W_EPI = 0;                       // warps 0-3: epilogue (warp % 4 = TMEM lane quarter), both accumulator buffers
+constexpr int CH_W_B = 4;                         // weight tiles
+constexpr int CH_W_MMA = 5;                       // warps 5, 6: MMA issuers; warp 5 owns the TMEM allocation
+constexpr int CH_W_A = 7;                         // warps 7-11: gathered rows, one whole 128-row slot at a time each
+constexpr int CH_A_WARPS = 5;
 constexpr int CH_DESC_WORDS = 48;                // sizeof(ConvDesc) / 4
 constexpr int CH_MAX_LAYERS = 16;                // layers per launch: the descriptors travel as kernel parameters (3 KB)
 
@@ -190,51 +184,41 @@ __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void *src, 
 }
 
 // ------------------------------------------------------------------------------------ the kernel
-template <bool PROF>
 __global__ void __launch_bounds__(CH_THREADS, 1)
-k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gbar, int sa0, int sa1, int sb, int bslot, int flags,
+k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gbar, int sa, int sb, int bslot, int flags,
              long long *dbg_clock) {
   extern __shared__ uint8_t smem_raw[];
   // All hot-loop addressing is done on 32-bit shared-window addresses computed once; the few generic accesses (descriptor,
   // BN constants) use pointers derived from smem_raw by an offset, so that the compiler keeps them in the shared space.
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int npipe = sa1 > 0 ? 2 : 1;
-  // the pipeline this warp works for (epilogue warps serve both)
-  const int P = (warp == CH_W_B + 1 || warp == CH_W_MMA + 2 || warp == CH_W_MMA + 3 || warp >= CH_W_A + CH_A_WARPS) ? 1 : 0;
-  const int sa = P ? sa1 : sa0;                                              // row slots of my pipeline's ring
   const uint32_t raw_u32 = smem_u32(smem_raw);
   const uint32_t base_u32 = (raw_u32 + 1023u) & ~1023u;                      // 1024-byte aligned: 128B-swizzle atoms
   uint8_t *smem = smem_raw + (base_u32 - raw_u32);
-  const uint32_t a_ring = base_u32;                                          // row slots: pipeline 0's, then pipeline 1's
-  const uint32_t b_ring = a_ring + (uint32_t)(sa0 + sa1) * CH_A_BYTES;       // weight slots (bslot is a multiple of 1024)
-  const uint32_t stg_u32 = b_ring + (uint32_t)(npipe * sb) * (uint32_t)bslot;   // epilogue staging: 4 warps x 4 KB
-  uint32_t a_ring_k = a_ring + (P ? (uint32_t)sa0 * CH_A_BYTES : 0u), b_ring_k = b_ring + (P ? (uint32_t)sb * (uint32_t)bslot : 0u);
+  const uint32_t a_ring = base_u32;                                          // row slots
+  const uint32_t b_ring = a_ring + (uint32_t)sa * CH_A_BYTES;                // weight slots (bslot is a multiple of 1024)
+  const uint32_t stg_u32 = b_ring + (uint32_t)sb * (uint32_t)bslot;          // epilogue staging: 4 warps x 4 KB
+  uint32_t a_ring_k = a_ring, b_ring_k = b_ring;
   CH_KEEP(a_ring_k); CH_KEEP(b_ring_k);
   uint8_t *aux = smem + (stg_u32 - base_u32) + CH_STG_BYTES;
   float *s_ss = reinterpret_cast<float *>(aux);                              // [scale x CH_SS_FLOATS | shift x CH_SS_FLOATS]
   uint64_t *bars = reinterpret_cast<uint64_t *>(s_ss + 2 * CH_SS_FLOATS);
-  uint32_t *s_misc = reinterpret_cast<uint32_t *>(bars + 2 * CH_BARS);       // [0] TMEM base
+  uint32_t *s_misc = reinterpret_cast<uint32_t *>(bars + 40);                // [0] TMEM base
 
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (flags & 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  constexpr bool prof = PROF;                      // per-role cycle accounting: a separate instantiation (it costs ~10 registers)
+  const bool prof = dbg_clock != nullptr;
   long long pw0 = 0, pw1 = 0, pw2 = 0, pt = 0;     // cycles in this role's waits (up to three kinds) and in its loop
-  if (prof && tid == 0) dbg_clock[blockIdx.x * 96 + 80] = clock64();
-  const uint32_t bars0 = smem_u32(bars);
-  uint32_t fullA = bars0 + (uint32_t)P * (CH_BARS * 8), emptyA = fullA + 8 * 8, fullB = fullA + 16 * 8, emptyB = fullA + 20 * 8;
-  uint32_t accFull = fullA + 24 * 8, accEmpty = fullA + 25 * 8;
+  if (dbg_clock && tid == 0) dbg_clock[blockIdx.x * 32 + 0] = clock64();
+  uint32_t fullA = smem_u32(bars), emptyA = fullA + 12 * 8, fullB = fullA + 24 * 8, emptyB = fullA + 28 * 8;
+  uint32_t accFull = fullA + 32 * 8, accEmpty = fullA + 34 * 8;
   CH_KEEP(fullA); CH_KEEP(emptyA); CH_KEEP(fullB); CH_KEEP(emptyB); CH_KEEP(accFull); CH_KEEP(accEmpty);
 
   if (tid == 0) {
-    for (int pp = 0; pp < 2; ++pp) {
-      const uint32_t bb = bars0 + (uint32_t)pp * (CH_BARS * 8);
-      for (int s = 0; s < 8; ++s) { mbar_init(bb + 8 * s, 32); mbar_init(bb + 8 * (8 + s), 1); }     // fullA: the 32 lanes of the slot's warp
-      for (int s = 0; s < 4; ++s) { mbar_init(bb + 8 * (16 + s), 1); mbar_init(bb + 8 * (20 + s), 2); }   // emptyB: one arrival per issuer
-      mbar_init(bb + 8 * 24, 2);                                                                        // accFull: both issuers
-      mbar_init(bb + 8 * 25, 4);                                                                        // accEmpty: four epilogue warps
-    }
+    for (int s = 0; s < sa; ++s) { mbar_init(fullA + 8 * s, 32); mbar_init(emptyA + 8 * s, 1); }   // fullA: the 32 lanes of the slot's warp
+    for (int s = 0; s < sb; ++s) { mbar_init(fullB + 8 * s, 1); mbar_init(emptyB + 8 * s, 2); }   // emptyB: one arrival per issuer
+    for (int b = 0; b < 2; ++b) { mbar_init(accFull + 8 * b, 2); mbar_init(accEmpty + 8 * b, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == CH_W_MMA) {   // all 512 TMEM columns: 256 per pipeline = two sub-tile accumulators of up to 128 columns, or one of 256
+  if (warp == CH_W_MMA) {   // all 512 TMEM columns: two accumulator buffers of 256 columns (one CTA per SM, no contention)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_misc[0])), "r"(512u));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -246,21 +230,19 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
   // Everything above touched no data of an earlier kernel in the stream; from here on we read activations.
   if (flags & 1) asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t tmem_base = s_misc[0];
-  if (prof && tid == 0) dbg_clock[blockIdx.x * 96 + 81] = clock64();
+  if (dbg_clock && tid == 0) dbg_clock[blockIdx.x * 32 + 1] = clock64();
 
   // pipeline state of this thread's role; persists over items and layers
   uint32_t a_slot = 0, a_phase = 0, b_slot = 0, b_phase = 0, n_item = 0;
-  uint32_t e_item0 = 0, e_item1 = 0;               // epilogue: items drained per pipeline
-  uint32_t g_slot = 0;                             // gather producers: row slots the pipeline has gone through before the current item
-  const int gw = warp >= CH_W_A ? (warp - CH_W_A) % CH_A_WARPS : 0;   // gather producers: index within the pipeline
-  uint32_t p_sl = (uint32_t)gw, p_lapb = 0, p_par = 0;   // gather producers: my next ring slot, global index of slot 0 of its lap, lap parity
+  uint32_t g_slot = 0;                             // gather producers: row slots the CTA has gone through before the current item
+  uint32_t p_sl = warp >= CH_W_A ? (uint32_t)(warp - CH_W_A) : 0u, p_lapb = 0, p_par = 0;   // gather producers: my next ring slot, global index of slot 0 of its lap, lap parity
 
   for (int L = 0; L < n_layers; ++L) {
     __syncthreads();                                   // every role is done with the previous layer (and with s_ss)
     const ConvDesc *s_desc = &args.d[L];               // parameter space: uniform loads
     const int d_K = s_desc->K, d_nb0 = s_desc->nb0, d_nb1 = s_desc->nb1, d_nt = s_desc->nt, d_n_ntiles = s_desc->n_ntiles;
     const int d_m_tiles = s_desc->m_tiles, d_nsplit = s_desc->nsplit, d_nsub_max = s_desc->nsub_max, d_sps = s_desc->stages_per_split;
-    const int d_n_out = (int)s_desc->n_out;                 // < 2^31 (checked by osb_conv_desc_fill)
+    const int64_t d_n_out = s_desc->n_out;
     {                                                  // folded BN constants of the layer -> shared memory
       const int nss = s_desc->cmap ? s_desc->cmap_cout : s_desc->cout;
       const float *sc = s_desc->scale, *sh = s_desc->shift;
@@ -277,28 +259,21 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
 
     const int nb = d_nb0 + d_nb1;
     const int T = d_K * nb;                                            // stages of one full (offset, channel block) sweep
-    const int U = d_m_tiles * d_n_ntiles * d_nsplit;                   // work units of the layer (< 2^31 / grid: checked on the host)
-    const int u_begin = (int)((int64_t)U * blockIdx.x / gridDim.x), u_end = (int)((int64_t)U * (blockIdx.x + 1) / gridDim.x);
+    const int64_t U = (int64_t)d_m_tiles * d_n_ntiles * d_nsplit;      // work units of the layer
+    const int64_t u_begin = U * blockIdx.x / gridDim.x, u_end = U * (blockIdx.x + 1) / gridDim.x;
     const int per_z = d_m_tiles * d_n_ntiles;
     const uint32_t b_bytes = (uint32_t)d_nt * 128u;
-    // The CTA's units are halved between the pipelines (contiguous ranges).  Pipeline 1 starts with a single-sub-tile item
-    // so that the two pipelines do not reach their item boundaries (accumulator hand-over to the epilogue) together.
-    const int u_mid = npipe == 2 ? u_begin + (u_end - u_begin + 1) / 2 : u_end;
-    const int pu_begin = P ? u_mid : u_begin, pu_end = P ? u_end : u_mid;
-    const bool stagger = !(flags & 0x20000);           // tuning bit 9: no staggered start
 
     // item = 1 or 2 consecutive units (same split, same N tile, adjacent row tiles) sharing every weight tile
-#define CH_ITEM_AT(u_, ub_, ue_, stag_)                                                                         \
-      const int z = (u_) / per_z, r_ = (u_) - z * per_z, nti = r_ / d_m_tiles,           \
-          m = r_ - nti * d_m_tiles,                                                                             \
-          nsub = (d_nsub_max == 2 && (u_) + 1 < (ue_) && m + 1 < d_m_tiles && !((stag_) && (u_) == (ub_))) ? 2 : 1,   \
-          t_begin = min(z * d_sps, T), t_end = min(t_begin + d_sps, T)
-#define CH_FOR_ITEMS()                                                                                          \
-    for (int u = pu_begin, _n; u < pu_end; u += _n)                                                             \
-      if (CH_ITEM_AT(u, pu_begin, pu_end, P == 1 && stagger); (_n = nsub, true))
+#define CH_FOR_ITEMS()                                                                                         \
+    for (int64_t u = u_begin, _n; u < u_end; u += _n)                                                          \
+      if (const int z = (int)(u / per_z), r_ = (int)(u - (int64_t)z * per_z), nti = r_ / d_m_tiles,            \
+          m = r_ - nti * d_m_tiles, nsub = (d_nsub_max == 2 && u + 1 < u_end && m + 1 < d_m_tiles) ? 2 : 1,    \
+          t_begin = min(z * d_sps, T), t_end = min(t_begin + d_sps, T);                                        \
+          (_n = nsub, true))
 
     const long long _role_t0 = prof ? clock64() : 0;
-    if (warp == CH_W_B || warp == CH_W_B + 1) {
+    if (warp == CH_W_B) {
       // ============================ weight tiles ====================================
       const uint8_t *wtiles = s_desc->wtiles;
       CH_FOR_ITEMS() {
@@ -318,26 +293,27 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
           if (++b_slot == (uint32_t)sb) { b_slot = 0; b_phase ^= 1; }
         }
       }
-    } else if (warp >= CH_W_MMA && warp < CH_W_MMA + 4) {
-      // ============ MMA issuers: the pipeline's first issuer owns sub-tile 0 of every item, the second sub-tile 1 ===============
+    } else if (warp == CH_W_MMA || warp == CH_W_MMA + 1) {
+      // ============ MMA issuers: warp CH_W_MMA owns sub-tile 0 of every item, the next warp sub-tile 1 ===============
       // One issuing thread spends ~64 cycles per tcgen05.mma plus ~400 cycles of barrier-wait / fence / commit per row
       // slot, more than the 288 cycles of tensor work a 96-channel slot carries; two issuers on disjoint accumulator
       // columns restore the slack two co-resident CTAs used to give.  Each sub-tile's MMAs are issued by one thread, in
       // stage order (bit-reproducible accumulation).
-      const int mi = (warp - CH_W_MMA) & 1;
+      const int mi = warp - CH_W_MMA;
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(d_nt >> 3) << 17) | ((uint32_t)(CH_M >> 4) << 24);
       CH_FOR_ITEMS() {
         (void)m; (void)nti;
+        const uint32_t buf = n_item & 1u;
         const bool mine = mi < nsub;
         // Both issuers follow the full protocol of every item, also the one without a sub-tile of its own (single-sub-tile
         // items): its arrivals on emptyB / accFull may only happen in the phase they belong to, i.e. after the same waits.
-        { CH_PROF_BEGIN(); mbar_wait(accEmpty, (n_item & 1u) ^ 1u); CH_PROF_END(pw2); }   // the epilogue drained the pipeline's accumulators
+        { CH_PROF_BEGIN(); mbar_wait(accEmpty + 8 * buf, ((n_item >> 1) & 1u) ^ 1u); CH_PROF_END(pw2); }   // the epilogue drained this buffer
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t dcol = tmem_base + (uint32_t)P * 256u + (uint32_t)mi * 128u;
+        const uint32_t dcol = tmem_base + buf * 256u + (uint32_t)mi * 128u;
         // two stages per iteration: the fixed cost of an iteration (waits, proxy fence, election, descriptor set-up) is a
         // dependent chain of a few hundred cycles; 12 MMAs behind it instead of 6
         for (int t = t_begin; t < t_end;) {
-          const int nst = min((flags & 0x8000) ? 1 : 2, t_end - t);       // tuning bit 7: one stage per iteration
+          const int nst = min(2, t_end - t);
           uint32_t sl[2], sph[2], bs[2], bph[2];
           {
             uint32_t as_ = a_slot + (uint32_t)mi, ap_ = a_phase, bs_ = b_slot, bp_ = b_phase;
@@ -409,8 +385,8 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
           }
           t += nst;
         }
-        if (mine) { if (elect_one()) umma_commit(accFull); }
-        else if (lane == 0) mbar_arrive(accFull);
+        if (mine) { if (elect_one()) umma_commit(accFull + 8 * buf); }
+        else if (lane == 0) mbar_arrive(accFull + 8 * buf);
         __syncwarp();
         ++n_item;
       }
@@ -420,7 +396,7 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
       // barrier wait and ONE (self-tracking) arrival; the destination carries the 128B swizzle (chunk ^ (row & 7)); a
       // missing neighbour is a zero-fill copy.  The slot's 128 row indices are four coalesced loads (lane l: rows l, l+32, ..)
       // fetched one slot of this warp ahead and handed round by shuffles.
-      const int w = gw, j = lane & 7, q = lane >> 3;
+      const int w = warp - CH_W_A, j = lane & 7, q = lane >> 3;
       const int32_t *nbr = s_desc->nbr;
       const uint8_t *src0 = s_desc->src0 + j * 16, *src1 = s_desc->src1 + j * 16;
       const uint32_t rb0 = (uint32_t)d_nb0 * 128u, rb1 = (uint32_t)d_nb1 * 128u;
@@ -442,7 +418,7 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
           const int32_t *nk = nbr ? nbr + (int64_t)k_ * d_n_out : nullptr;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const int o = (m + s_) * CH_M + 32 * i + lane;
+            const int64_t o = (int64_t)(m + s_) * CH_M + 32 * i + lane;
             r[i] = (o < d_n_out) ? (nk ? __ldg(nk + o) : (int32_t)o) : -1;
           }
         };
@@ -507,34 +483,14 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
       const int32_t *d_row_map = s_desc->out_row_map, *d_cmap = s_desc->cmap;
       auto lds128 = [](uint32_t a) { uint4 v; asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; };
       auto sts128 = [](uint32_t a, uint4 v) { asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); };
-      // Both pipelines' items, each pipeline's in its own order, whichever accumulator is complete first.
-      int eu0 = u_begin, eu1 = u_mid;
-      while (eu0 < u_mid || eu1 < u_end) {
-        int ep;
-        if (eu1 >= u_end) ep = 0;
-        else if (eu0 >= u_mid) ep = 1;
-        else {
-          CH_PROF_BEGIN();
-          const uint32_t f0 = bars0 + 24 * 8, f1 = f0 + CH_BARS * 8;
-          for (uint32_t it = 0;; ++it) {
-            const uint32_t ok0 = mbar_try(f0, e_item0 & 1u), ok1 = mbar_try(f1, e_item1 & 1u);
-            if (__any_sync(0xffffffffu, ok0)) { ep = 0; break; }
-            if (__any_sync(0xffffffffu, ok1)) { ep = 1; break; }
-            __nanosleep(128);
-            if (it > (1u << 24)) __trap();
-          }
-          CH_PROF_END(pw0);
-        }
-        const uint32_t eFull = bars0 + (uint32_t)ep * (CH_BARS * 8) + 24 * 8, eEmpty = eFull + 8;
-        { CH_PROF_BEGIN(); mbar_wait_relaxed(eFull, (ep ? e_item1 : e_item0) & 1u, 128); CH_PROF_END(pw0); }
+      CH_FOR_ITEMS() {
+        const uint32_t buf = n_item & 1u;
+        { CH_PROF_BEGIN(); mbar_wait_relaxed(accFull + 8 * buf, (n_item >> 1) & 1u, 128); CH_PROF_END(pw0); }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int eu = ep ? eu1 : eu0;
-        CH_ITEM_AT(eu, ep ? u_mid : u_begin, ep ? u_end : u_mid, ep == 1 && stagger);
-        (void)t_begin; (void)t_end;
         for (int s = 0; s < nsub; ++s) {
           const int64_t wrow0 = (int64_t)(m + s) * CH_M + q * 32;        // first global row of this warp
           const int64_t o = wrow0 + lane;
-          int32_t my_orow = (int32_t)min(o, (int64_t)d_n_out - 1);
+          int32_t my_orow = (int32_t)min(o, d_n_out - 1);
           if (d_row_map && o < d_n_out) my_orow = __ldg(d_row_map + o);
           // staged tile (32 rows x 128 B, swizzled) -> global, 4 full lines per instruction
           auto flush_tile = [&](uint8_t *base, int64_t row_bytes, int64_t col_byte, bool mapped) {
@@ -557,7 +513,7 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
             float y[32];
             {
               uint32_t v0[16], v1[16];
-              const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ep * 256u + (uint32_t)s * 128u + cbo * 32;
+              const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256u + (uint32_t)s * 128u + cbo * 32;
               tmem_ld16(taddr, v0);
               tmem_ld16(taddr + 16, v1);
               asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -640,12 +596,11 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
         // this warp's TMEM reads of the buffer are complete (tcgen05.wait::ld above): hand it back to the MMA warps
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(eEmpty);
-        if (ep) { ++e_item1; eu1 += nsub; } else { ++e_item0; eu0 += nsub; }
+        if (lane == 0) mbar_arrive(accEmpty + 8 * buf);
+        ++n_item;
       }
     }
 #undef CH_FOR_ITEMS
-#undef CH_ITEM_AT
     if (prof) pt += clock64() - _role_t0;
 
     if (d_nsplit > 1) {
@@ -696,9 +651,11 @@ k_conv_chain(const __grid_constant__ ChainArgs args, int n_layers, unsigned *gba
     }
   }
 
-  if (prof && tid == 0) dbg_clock[blockIdx.x * 96 + 82] = clock64();
-  if (prof && lane == 0) {      // per warp: [wait kind 0, wait kind 1, wait kind 2, role loop total]; CTA time stamps at 80..82
-    long long *o = dbg_clock + blockIdx.x * 96 + warp * 4;
+  if (dbg_clock && tid == 0) dbg_clock[blockIdx.x * 32 + 2] = clock64();
+  if (dbg_clock && lane == 0 && (warp == CH_W_B || warp == CH_W_MMA || warp == CH_W_MMA + 1 || warp == CH_W_A || warp == 0)) {
+    // rows of 4: [wait kind 0, wait kind 1, wait kind 2, role loop total]; B producer 4.., issuer0 8.., issuer1 12.., A producer 16.., epilogue 20..
+    const int base = warp == CH_W_B ? 4 : warp == CH_W_MMA ? 8 : warp == CH_W_MMA + 1 ? 12 : warp == CH_W_A ? 16 : 20;
+    long long *o = dbg_clock + blockIdx.x * 32 + base;
     o[0] = pw0; o[1] = pw1; o[2] = pw2; o[3] = pt;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -767,8 +724,7 @@ static int chain_nsplit(int64_t n_out, int K, int cin, int cout, int grid_ctas, 
 static int g_chain_force_split = 0;      // tuning: > 0 forces the split factor of every layer (1 disables splitting)
 static int g_chain_nsub = 2;             // tuning: 1 = never pair sub-tiles
 static int g_chain_grid = 0;             // tuning: CTAs per launch (0 = one per SM)
-static int g_chain_sa = 0, g_chain_sb = 0;   // tuning: ring depths (0 = as many row slots as fit / 2 weight slots per pipeline)
-static int g_chain_pipes = 2;            // tuning: 1 = a single pipeline per CTA (half of the role warps idle)
+static int g_chain_sa = 0, g_chain_sb = 0;   // tuning: ring depths (0 = as many row slots as fit / 3 or 2 weight slots)
 static long long *g_chain_dbg_clock = nullptr;
 static int g_chain_dbg_skip = 0;         // tuning: bit0 no row copies, bit1 no weight loads, bit2 no MMAs, bit3 no stores,
                                          // bit5 no tcgen05 fence, bit6 plain arrivals for commits, bit8 legacy (consumer-side) completion
@@ -780,7 +736,6 @@ int osb_tuning_set(const char *name, int64_t value) {
   else if (n == "chain_grid") g_chain_grid = (int)value;
   else if (n == "chain_sa") g_chain_sa = (int)value;
   else if (n == "chain_sb") g_chain_sb = (int)value;
-  else if (n == "chain_pipes") g_chain_pipes = (int)value;
   else if (n == "chain_dbg_clock") g_chain_dbg_clock = (long long *)(intptr_t)value;
   else if (n == "chain_dbg_skip") g_chain_dbg_skip = (int)value;
   else if (n == "chain_report") {               // host-mapped int64 buffer [1 + 4*1024]: where a stuck wait was (tuning)
@@ -852,8 +807,7 @@ int osb_conv_chain_launch(const void *descs_host, int32_t n_layers, void *grid_b
     OSB_CHECK(i == 0 || h[i].barrier_before || h[i].nsplit == 1 || h[i - 1].nsplit == 1 || h[i].partial != h[i - 1].partial,
               "osb_conv_chain_launch: layers %d and %d share a split workspace without a barrier between them", i - 1, i);
   }
-  OSB_SMEM_ATTR_ONCE(k_conv_chain<false>, 227 * 1024);
-  if (g_chain_dbg_clock) { OSB_SMEM_ATTR_ONCE(k_conv_chain<true>, 227 * 1024); }
+  OSB_SMEM_ATTR_ONCE(k_conv_chain, 227 * 1024);
   const int grid = osb_conv_chain_grid();
   // the layer descriptors travel as kernel parameters: at most CH_MAX_LAYERS per launch, longer lists in several launches
   // (a launch boundary orders everything, so the first layer of a later launch needs no grid barrier)
@@ -869,38 +823,26 @@ int osb_conv_chain_launch(const void *descs_host, int32_t n_layers, void *grid_b
     }
     OSB_CHECK(!need_bar || grid_barrier_dev != nullptr, "osb_conv_chain_launch: this chain needs the grid-barrier words");
     const int bslot = nt_max * 128;
-    const int fixed = 1024 + CH_STG_BYTES + 2 * CH_SS_FLOATS * 4 + 2 * CH_BARS * 8 + 64;   // alignment slack, staging, BN constants, barriers
-    const int npipe = g_chain_pipes == 1 ? 1 : 2;
-    int sb = g_chain_sb > 0 ? g_chain_sb : (npipe == 2 ? 2 : (bslot >= 32768 ? 2 : 3));       // weight slots per pipeline
+    const int fixed = 1024 + CH_STG_BYTES + 2 * CH_SS_FLOATS * 4 + 40 * 8 + 64;   // alignment slack, staging, BN constants, barriers
+    int sb = g_chain_sb > 0 ? g_chain_sb : (bslot >= 32768 ? 2 : 3);
     sb = std::min(sb, CH_MAX_SB);
-    int sa = (227 * 1024 - fixed - npipe * sb * bslot) / CH_A_BYTES;                            // row slots, both pipelines
+    int sa = (227 * 1024 - fixed - sb * bslot) / CH_A_BYTES;
     if (g_chain_sa > 0) sa = std::min(sa, g_chain_sa);
-    sa = std::min(sa, npipe * CH_MAX_SA);
-    OSB_CHECK(sa >= 2 * npipe, "osb_conv_chain_launch: shared memory does not hold two row slots per pipeline");
-    // Every ring gets an EVEN number of row slots: with two sub-tiles per stage a slot (and its two barriers) then always belongs to
-    // the same issuer.  With an odd ring the slots alternate between the two issuers from lap to lap; that variant produced stale
-    // rows on hardware in pipeline 1 (profiles/r02_chain_roles.md), as did the four-issuer kernel with a seven-slot ring.
-    // (tuning bit 10 of chain_dbg_skip lifts the rule.)  Four gather warps per pipeline: rings of 8, 4 or 2 slots keep their load even.
-    int sa0 = npipe == 2 ? (sa + 1) / 2 : sa, sa1 = sa - sa0;
-    if (!(g_chain_dbg_skip & 0x400)) {
-      const int per = sa / npipe;
-      sa0 = per >= 8 ? 8 : per >= 4 ? 4 : 2;
-      sa1 = npipe == 2 ? sa0 : 0;
-    }
-    sa = sa0 + sa1;
-    const size_t smem_bytes = (size_t)sa * CH_A_BYTES + (size_t)npipe * sb * bslot + fixed;
+    sa = std::min(sa, CH_MAX_SA);
+    // An EVEN ring: with two sub-tiles per stage every row slot (and its two barriers) then belongs to one issuer for good.
+    // With an odd ring the slots alternate between the issuers from lap to lap; a two-pipeline variant of this kernel produced
+    // intermittently stale rows on hardware exactly then (and never with even rings): profiles/r02_chain_roles.md.
+    sa &= ~1;
+    OSB_CHECK(sa >= 4, "osb_conv_chain_launch: shared memory does not hold four row slots");
+    const size_t smem_bytes = (size_t)sa * CH_A_BYTES + (size_t)sb * bslot + fixed;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(CH_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
     cfg.attrs = attr; cfg.numAttrs = (flags & 1) ? 1 : 0;
-    const int kflags = (int)((flags & 1) | (g_chain_dbg_skip << 8));
-    if (g_chain_dbg_clock) {
-      OSB_CUDA(cudaLaunchKernelEx(&cfg, k_conv_chain<true>, args, (int)cnt, (unsigned *)grid_barrier_dev, sa0, sa1, sb, bslot, kflags, g_chain_dbg_clock));
-    } else {
-      OSB_CUDA(cudaLaunchKernelEx(&cfg, k_conv_chain<false>, args, (int)cnt, (unsigned *)grid_barrier_dev, sa0, sa1, sb, bslot, kflags, (long long *)nullptr));
-    }
+    OSB_CUDA(cudaLaunchKernelEx(&cfg, k_conv_chain, args, (int)cnt, (unsigned *)grid_barrier_dev, sa, sb, bslot,
+                                (int)((flags & 1) | (g_chain_dbg_skip << 8)), g_chain_dbg_clock));
     OSB_LAUNCH_CHECK();
   }
   return 0;

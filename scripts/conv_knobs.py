@@ -41,7 +41,7 @@ def timed(fn, reps=20):
 print(f'# {workload} n={n} {cin}->{cout} k={ks}')
 print(f'legacy k_conv_tc                         {timed(lambda: tc.conv_tc(x, cin, None, 0, nbr, n, ks ** 3, wp, cout)):8.1f} us')
 SETS = [
-    ('chain default (two pipelines)', {}),
+    ('chain default (noinc arrivals, consumer-side fence)', {}),
 
     ('nsub=1', {'chain_nsub': 1}),
     ('no A,B,MMA (0x7)', {'chain_dbg_skip': 0x7}),
@@ -50,14 +50,12 @@ SETS = [
     ('no B (0x2)', {'chain_dbg_skip': 0x2}),
     ('no MMA (0x4)', {'chain_dbg_skip': 0x4}),
     ('no stores (0x8)', {'chain_dbg_skip': 0x8}),
-    ('one pipeline', {'chain_pipes': 1}),
-    ('one stage per issue iteration (0x80)', {'chain_dbg_skip': 0x80}),
-    ('sb=3 per pipeline', {'chain_sb': 3}),
-    ('sa=6 (3+3)', {'chain_sa': 6}),
+    ('sa=5', {'chain_sa': 5}),
+    ('sa=7', {'chain_sa': 7}),
     ('end', {}),
 ]
 for name, knobs in SETS[:-1]:
-    for k_, v_ in (('chain_dbg_skip', 0), ('chain_nsub', 2), ('chain_sa', 0), ('chain_sb', 0), ('chain_pipes', 2)):
+    for k_, v_ in (('chain_dbg_skip', 0), ('chain_nsub', 2), ('chain_sa', 0)):
         tc.tuning_set(k_, v_)
     for k_, v_ in knobs.items():
         tc.tuning_set(k_, v_)

@@ -28,25 +28,20 @@ grid = C.lib().osb_conv_chain_grid()
 run = lambda: tc.conv_chain_single(x, cin, None, 0, nbr, n, ks ** 3, wt, cout)
 for _ in range(3):
     run()
-buf = torch.zeros(grid * 96, dtype=torch.int64, device=dev)
+buf = torch.zeros(grid * 32, dtype=torch.int64, device=dev)
 tc.tuning_set('chain_dbg_clock', buf.data_ptr())
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 a.record(); run(); b.record()
 torch.cuda.synchronize()
 tc.tuning_set('chain_dbg_clock', 0)
-d = buf.view(grid, 96).double().cpu()
+d = buf.view(grid, 32).double().cpu()
 print(f'# {workload} n={n} {cin}->{cout} k={ks} knobs={knobs}: {a.elapsed_time(b) * 1e3:.1f} us with accounting on')
-tot = (d[:, 82] - d[:, 80])
-print(f'CTA cycles: mean {tot.mean():.0f} max {tot.max():.0f}; set-up {(d[:, 81] - d[:, 80]).mean():.0f}')
-# per warp: [wait 0, wait 1, wait 2, loop]; warps 0-3 epilogue, 4/5 weights of pipeline 0/1, 6,7 / 8,9 issuers, 10-13 / 14-17 gather
-rows = [('epilogue w0', 0, ('wait accFull', '-', '-')),
-        ('weights P0', 4, ('wait emptyB', '-', '-')), ('weights P1', 5, ('wait emptyB', '-', '-')),
-        ('issuer P0 s0', 6, ('-', 'wait fullA/B', 'wait accEmpty')), ('issuer P0 s1', 7, ('-', 'wait fullA/B', 'wait accEmpty')),
-        ('issuer P1 s0', 8, ('-', 'wait fullA/B', 'wait accEmpty')), ('issuer P1 s1', 9, ('-', 'wait fullA/B', 'wait accEmpty')),
-        ('gather P0 w0', 10, ('wait emptyA', 'index loads land', '-')), ('gather P0 w3', 13, ('wait emptyA', 'index loads land', '-')),
-        ('gather P1 w0', 14, ('wait emptyA', 'index loads land', '-')), ('gather P1 w3', 17, ('wait emptyA', 'index loads land', '-'))]
-for name, wp, labels in rows:
-    base = wp * 4
+tot = (d[:, 2] - d[:, 0])
+print(f'CTA cycles: mean {tot.mean():.0f} max {tot.max():.0f}; set-up {(d[:, 1] - d[:, 0]).mean():.0f}')
+rows = [('B producer', 4, ('wait emptyB', '-', '-')), ('issuer 0', 8, ('wait fullB', 'wait fullA', 'wait accEmpty')),
+        ('issuer 1', 12, ('wait fullB', 'wait fullA', 'wait accEmpty')), ('gather producer (1 of 5 warps)', 16, ('wait emptyA', 'index loads land', '-')),
+        ('epilogue (1 of 4 warps)', 20, ('wait accFull', '-', '-'))]
+for name, base, labels in rows:
     w0, w1, w2, t = (d[:, base + i].mean().item() for i in range(4))
     parts = ', '.join(f'{lab} {v:.0f}' for lab, v in zip(labels, (w0, w1, w2)) if lab != '-')
-    print(f'{name:14s} loop {t:9.0f}  | {parts} | own work {t - w0 - w1 - w2:9.0f}')
+    print(f'{name:22s} loop {t:9.0f}  | {parts} | own work {t - w0 - w1 - w2:9.0f}')
