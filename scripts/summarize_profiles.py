@@ -9,10 +9,14 @@ import subprocess
 import sys
 
 
-def launches(path, out, title):
+def launches(path, out, title, last=0, drop_tail=0):
     lines = open(path).read().splitlines()
     start = [i for i, l in enumerate(lines) if l.startswith('"ID"')][0]
     rows = list(csv.DictReader(lines[start:]))
+    if drop_tail:                              # launches after the step (bench bookkeeping)
+        rows = rows[:-drop_tail]
+    if last:                                   # only the last `last` launches (one step of a multi-step capture)
+        rows = rows[-last:]
     agg = collections.defaultdict(lambda: [0, 0.0])
     for r in rows:
         n = r['Kernel Name'].split('(')[0].replace('void ', '')
@@ -24,9 +28,10 @@ def launches(path, out, title):
                 f'compare SHARES, not absolutes).\n\n{len(rows)} launches, {tot / 1e3:.1f} us total.\n\n| kernel | launches | total us | share |\n|---|---:|---:|---:|\n')
         for n, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
             f.write(f'| `{n[:100]}` | {c} | {t / 1e3:.1f} | {100 * t / tot:.1f}% |\n')
-        seq = [(r['Grid Size'], float(r['Metric Value']) / 1e3) for r in rows if 'k_conv_tc' in r['Kernel Name']]
-        if seq:
-            f.write('\n`k_conv_tc` launches in order (grid: us):\n\n```\n' + ' '.join(f"{g}:{t:.0f}" for g, t in seq) + '\n```\n')
+        for kn in ('k_conv_tc', 'k_conv_chain'):
+            seq = [(r['Grid Size'], float(r['Metric Value']) / 1e3) for r in rows if kn in r['Kernel Name']]
+            if seq:
+                f.write(f'\n`{kn}` launches in order (grid: us):\n\n```\n' + ' '.join(f"{g}:{t:.0f}" for g, t in seq) + '\n```\n')
 
 
 KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'dram__throughput.avg.pct_of_peak_sustained_elapsed',
@@ -61,4 +66,7 @@ def full(path, out, title):
 if __name__ == '__main__':
     mode, src, out = sys.argv[1:4]
     title = sys.argv[4] if len(sys.argv) > 4 else src
-    (launches if mode == 'launches' else full)(src, out, title)
+    if mode == 'launches':
+        launches(src, out, title, int(sys.argv[5]) if len(sys.argv) > 5 else 0, int(sys.argv[6]) if len(sys.argv) > 6 else 0)
+    else:
+        full(src, out, title)
