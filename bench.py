@@ -256,8 +256,9 @@ def run_distill(args, rank, local, world):
             evs.append((a, b))
         torch.cuda.synchronize()
         gc.enable()
-        ts = sorted(a.elapsed_time(b) for a, b in evs)
-        return sum(ts), {'min': ts[0], 'median': ts[len(ts) // 2], 'max': ts[-1]}
+        seq = [a.elapsed_time(b) for a, b in evs]
+        ts = sorted(seq)
+        return sum(ts), {'min': ts[0], 'median': ts[len(ts) // 2], 'max': ts[-1], 'in_order': [round(t, 2) for t in seq[:64]]}
 
     def barrier():
         if world > 1:
