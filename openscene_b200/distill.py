@@ -64,7 +64,9 @@ def distill_step(model, optimizer, coords, feats, feat_3d, mask, loss_type='cosi
 def wrap_ddp(model, device=None):
     if dist.is_initialized() and dist.get_world_size() > 1:
         ids = [device.index] if device is not None and device.type == 'cuda' else None
-        return torch.nn.parallel.DistributedDataParallel(model, device_ids=ids)
+        # gradients live inside the all-reduce buckets (no copy in / out), 16 MB buckets: the first all-reduce starts after the
+        # decoder's gradients, the last (exposed) one carries the stem and the first encoder stage only
+        return torch.nn.parallel.DistributedDataParallel(model, device_ids=ids, gradient_as_bucket_view=True, bucket_cap_mb=16)
     return model
 
 
