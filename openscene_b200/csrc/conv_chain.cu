@@ -713,12 +713,35 @@ int osb_conv_pack_weight_tiles(const float *w, int32_t K, int32_t cin, int32_t c
   return 0;
 }
 
-// Split factor and scratch of one layer when it runs on a grid of `grid_ctas` CTAs.
-static int chain_nsplit(int64_t n_out, int K, int cin, int cout, int grid_ctas, int force) {
+// Split factor of one layer when it runs on a grid of `grid_ctas` CTAs: the candidate with the lowest modelled time.
+//   main loop   items per CTA x stages per split x ~0.56 us (1.4x for 256-wide N tiles); an item is two row-adjacent units
+//               when the N tile is <= 128 wide (two issuers run them side by side), so what counts is ceil(units per CTA / 2)
+//   split cost  ~8 us (grid barrier, partial tiles out, reduce pass) + the partials written and read once at ~3 TB/s
+// Fitted on the per-layer times of the bench scene (scripts/layer_times.py, OSB_CHAIN_MAX_TILES=0): the former rule
+// `grid / tiles` left half of the SMs idle on 76-tile levels (9.7 k rows: one unit of 108 stages per busy CTA).
+static int chain_nsplit(int64_t n_out, int K, int cin, int cout, int grid_ctas, int force, int nsub_knob) {
   const int cp = chain_cout_pad(cout), nt = chain_nt(cout);
   const int64_t tiles = ceil_div(n_out, CH_M) * (cp / nt);
-  int nsplit = force > 0 ? force : (int)(grid_ctas / tiles);
-  return std::max(1, std::min(nsplit, std::min(32, K * (cin / 32))));
+  const int T = K * (cin / 32);
+  const int cap = std::max(1, std::min(32, T));
+  if (force > 0) return std::min(force, cap);
+  const bool pairs = nt <= 128 && nsub_knob >= 2;
+  double best = 1e30;
+  int best_ns = 1;
+  for (int ns = 1; ns <= cap; ++ns) {
+    const int sps = (T + ns - 1) / ns;
+    if ((T + sps - 1) / sps != ns) continue;                       // this many splits would leave empty ones
+    const int64_t upc = ceil_div(tiles * ns, (int64_t)grid_ctas);
+    const int64_t items = pairs ? (upc + 1) / 2 : upc;
+    double us = (double)items * sps * 0.56 * (nt > 128 ? 1.4 : 1.0);
+    if (ns > 1) {
+      const double partial_bytes = (double)ns * (double)n_out * cp * 4.0;
+      if (partial_bytes > 64e6) continue;                          // scratch stays small (the engine provides 96 MB per layer)
+      us += 8.0 + 2.0 * partial_bytes / 3e6;
+    }
+    if (us < best - std::max(0.5, 0.08 * best)) { best = us; best_ns = ns; }   // fewer splits unless the model sees a clear gain
+  }
+  return best_ns;
 }
 
 static int g_chain_force_split = 0;      // tuning: > 0 forces the split factor of every layer (1 disables splitting)
@@ -754,7 +777,7 @@ int osb_conv_chain_grid(void) {
 }
 
 size_t osb_conv_chain_workspace_bytes(int64_t n_out, int32_t K, int32_t cin, int32_t cout) {
-  const int ns = chain_nsplit(n_out, K, cin, cout, osb_conv_chain_grid(), g_chain_force_split);
+  const int ns = chain_nsplit(n_out, K, cin, cout, osb_conv_chain_grid(), g_chain_force_split, g_chain_nsub);
   return ns > 1 ? (size_t)ns * n_out * chain_cout_pad(cout) * sizeof(float) : 0;
 }
 
@@ -783,7 +806,7 @@ int osb_conv_desc_fill(void *desc_host, const void *src0, int32_t c0, const void
   d.relu = relu; d.cmap_cout = cmap_cout; d.m_tiles = (int)ceil_div(n_out, CH_M);
   d.nsub_max = (d.nt <= 128 && g_chain_nsub >= 2) ? 2 : 1;
   d.barrier_before = barrier_before ? 1 : 0;
-  d.nsplit = cmap ? 1 : chain_nsplit(n_out, K, cin, cout, osb_conv_chain_grid(), g_chain_force_split);
+  d.nsplit = cmap ? 1 : chain_nsplit(n_out, K, cin, cout, osb_conv_chain_grid(), g_chain_force_split, g_chain_nsub);
   const int T = K * (cin / 32);
   d.stages_per_split = (T + d.nsplit - 1) / d.nsplit;
   d.nsplit = (T + d.stages_per_split - 1) / d.stages_per_split;            // no empty splits
