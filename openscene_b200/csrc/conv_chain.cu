@@ -713,12 +713,14 @@ int osb_conv_pack_weight_tiles(const float *w, int32_t K, int32_t cin, int32_t c
   return 0;
 }
 
-// Split factor of one layer when it runs on a grid of `grid_ctas` CTAs: the candidate with the lowest modelled time.
-//   main loop   items per CTA x stages per split x ~0.56 us (1.4x for 256-wide N tiles); an item is two row-adjacent units
-//               when the N tile is <= 128 wide (two issuers run them side by side), so what counts is ceil(units per CTA / 2)
-//   split cost  ~8 us (grid barrier, partial tiles out, reduce pass) + the partials written and read once at ~3 TB/s
-// Fitted on the per-layer times of the bench scene (scripts/layer_times.py, OSB_CHAIN_MAX_TILES=0): the former rule
-// `grid / tiles` left half of the SMs idle on 76-tile levels (9.7 k rows: one unit of 108 stages per busy CTA).
+// Split factor of one layer when it runs on a grid of `grid_ctas` CTAs.  Base rule: as many splits as it takes to give every
+// CTA a unit (grid / tiles).  That rule leaves half of the SMs idle on 76-tile levels (9.7 k rows: one unit of 108 stages per
+// busy CTA), so a small cost model may RAISE the factor when it predicts a clear gain (it never lowers it: for the smallest
+// levels the measured optimum is the base rule):
+//   main loop   per CTA (pairs of units x ~0.75 us + single units x ~0.6 us) x stages per split; an item is two row-adjacent
+//               units when the N tile is <= 128 wide (two issuers run them side by side); 1.6x for 256-wide N tiles
+//   split cost  ~10 us (grid barrier, partial tiles out, reduce pass) + the partials written and read once at ~5 TB/s (L2)
+// Constants fitted on the per-layer times of the bench scene (scripts/layer_times.py with OSB_CHAIN_MAX_TILES=0).
 static int chain_nsplit(int64_t n_out, int K, int cin, int cout, int grid_ctas, int force, int nsub_knob) {
   const int cp = chain_cout_pad(cout), nt = chain_nt(cout);
   const int64_t tiles = ceil_div(n_out, CH_M) * (cp / nt);
@@ -726,20 +728,26 @@ static int chain_nsplit(int64_t n_out, int K, int cin, int cout, int grid_ctas, 
   const int cap = std::max(1, std::min(32, T));
   if (force > 0) return std::min(force, cap);
   const bool pairs = nt <= 128 && nsub_knob >= 2;
-  double best = 1e30;
-  int best_ns = 1;
-  for (int ns = 1; ns <= cap; ++ns) {
+  const int base = (int)std::max<int64_t>(1, std::min<int64_t>(grid_ctas / tiles, cap));
+  auto cost = [&](int ns, bool &ok) {
     const int sps = (T + ns - 1) / ns;
-    if ((T + sps - 1) / sps != ns) continue;                       // this many splits would leave empty ones
+    ok = (T + sps - 1) / sps == ns;                                // else this many splits would leave empty ones
     const int64_t upc = ceil_div(tiles * ns, (int64_t)grid_ctas);
-    const int64_t items = pairs ? (upc + 1) / 2 : upc;
-    double us = (double)items * sps * 0.56 * (nt > 128 ? 1.4 : 1.0);
+    const double per = pairs ? (double)(upc / 2) * 0.75 + (double)(upc % 2) * 0.6 : (double)upc * 0.6 * 1.6;
+    double us = per * sps + 4.0;
     if (ns > 1) {
       const double partial_bytes = (double)ns * (double)n_out * cp * 4.0;
-      if (partial_bytes > 64e6) continue;                          // scratch stays small (the engine provides 96 MB per layer)
-      us += 8.0 + 2.0 * partial_bytes / 3e6;
+      if (partial_bytes > 64e6) ok = false;                        // scratch stays small (the engine provides 96 MB per layer)
+      us += 10.0 + 2.0 * partial_bytes / 5e6;
     }
-    if (us < best - std::max(0.5, 0.08 * best)) { best = us; best_ns = ns; }   // fewer splits unless the model sees a clear gain
+    return us;
+  };
+  bool ok = true;
+  double best = cost(base, ok);
+  int best_ns = base;
+  for (int ns = base + 1; ns <= cap; ++ns) {
+    const double us = cost(ns, ok);
+    if (ok && us < best - std::max(0.5, 0.08 * best)) { best = us; best_ns = ns; }
   }
   return best_ns;
 }
