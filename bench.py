@@ -266,7 +266,10 @@ def run_distill(args, rank, local, world):
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local, dev) if rank == 0 else None
-    for _ in range(max(args.warmup, 3)):
+    # at least 10 untimed steps: DDP rebuilds its buckets after the first iteration, NCCL sets its channels up lazily, and the
+    # random translation changes the coarse-level sizes from step to step until the caching allocator has seen the range
+    n_warm = max(args.warmup, 10)
+    for _ in range(n_warm):
         step()
     barrier()
     l0 = _cabi.lib().osb_launch_count()
@@ -297,7 +300,7 @@ def run_distill(args, rank, local, world):
         n_par = sum(p.numel() for p in model.parameters())
         value = total_vox * args.steps / (t_all / 1e3)
         line = {'metric': 'voxels/s distillation step (fwd + cosine loss + bwd + Adam)', 'value': value, 'unit': 'voxels/s',
-                'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': t_all / args.steps,
+                'n_gpus': world, 'steps': args.steps, 'warmup': n_warm, 'ms_per_step': t_all / args.steps,
                 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': 'bf16x3 (split fp32 operands, fp32 accumulate); wgrad bf16x4', 'data': 'synthetic',
                 'config': {'workload': f'config3_distill: one config2_200k scene ({n0} voxels) per GPU, {arch}, 768-d head, '
