@@ -98,11 +98,12 @@ class FusedFeatureFile:
         if self.n_points < 0 or self.n_rows < 0 or self.channels <= 0 or self.row_stride < self.channels * 2 or \
                 size < self._rows_off + self.n_rows * self.row_stride:
             raise ValueError(f"{path}: truncated or inconsistent container")
-        self._map = np.memmap(path, dtype=np.uint8, mode='r')
+        self._map = np.memmap(path, dtype=np.uint8, mode='c')      # copy-on-write mapping: never written, but torch wants a writable buffer
         nb = (self.n_points + 7) // 8
         self._bitmap = np.asarray(self._map[self._mask_off:self._mask_off + nb])
         self._rows = self._map[self._rows_off:self._rows_off + self.n_rows * self.row_stride].view(self._np_dtype) \
             .reshape(self.n_rows, self.row_stride // 2)
+        self._rows_t = torch.from_numpy(self._rows)                 # zero-copy view of the mapping: index_select gathers with all host threads
         self._rank = None
         self._staging = None
 
@@ -151,10 +152,14 @@ class FusedFeatureFile:
         if rows.min() < 0 or rows.max() >= self.n_rows:
             raise ValueError("read_rows: row index out of range")
         stage = self._stage(n)
-        stage_np = stage.numpy()
+        idx = torch.from_numpy(rows)
+        src = self._rows_t if self.row_stride == self.channels * 2 else self._rows_t[:, :self.channels]
         for a in range(0, n, chunk_rows):
             b = min(n, a + chunk_rows)
-            np.take(self._rows[:, :self.channels], rows[a:b], axis=0, out=stage_np[a:b])
+            if src.is_contiguous():
+                torch.index_select(src, 0, idx[a:b], out=stage[a:b])
+            else:
+                stage[a:b] = src[idx[a:b]]
             out[a:b].copy_(stage[a:b], non_blocking=True)
         if dev.type == 'cuda':
             torch.cuda.current_stream(dev).synchronize()           # the staging buffer is reused by the next call
