@@ -34,7 +34,9 @@ k_rs_hist(const uint64_t *__restrict__ keys, int64_t n, int shift, int32_t *__re
   hist[(int64_t)threadIdx.x * n_tiles + blockIdx.x] = s_cnt[threadIdx.x];     // digit-major
 }
 
-// exclusive scan of `m` int32 values by one block (m = 256 * n_tiles, a few 10^4 .. 10^5); 8 values per thread per round
+// exclusive scan of `m` int32 values by one block (m = 256 * n_tiles, a few 10^4 .. 10^5).  A round covers 32 values per thread
+// (eight 16-byte loads in flight per thread, 32768 values per round): the radix-sort histograms of the bench scenes
+// (<= 128 tiles) take ONE round -- one load phase, one block scan, one store phase -- instead of four dependent ones.
 static __global__ void __launch_bounds__(1024)
 k_scan_single_block(int32_t *__restrict__ data, int64_t m) {
   __shared__ int32_t s_warp[32];
@@ -42,12 +44,21 @@ k_scan_single_block(int32_t *__restrict__ data, int64_t m) {
   if (threadIdx.x == 0) s_carry = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int64_t base = 0; base < m; base += 8192) {
-    const int64_t i0 = base + (int64_t)threadIdx.x * 8;
-    int32_t v[8];
+  const bool vec = (reinterpret_cast<uintptr_t>(data) & 15) == 0;
+  for (int64_t base = 0; base < m; base += 32768) {
+    const int64_t i0 = base + (int64_t)threadIdx.x * 32;
+    int32_t v[32];
+    if (vec && i0 + 32 <= m) {
+      const int4 *p = reinterpret_cast<const int4 *>(data + i0);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { const int4 t = p[q]; v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w; }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = (i0 + j < m) ? data[i0 + j] : 0;
+    }
     int32_t tot = 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { v[j] = (i0 + j < m) ? data[i0 + j] : 0; tot += v[j]; }
+    for (int j = 0; j < 32; ++j) tot += v[j];
     int32_t x = tot;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -69,7 +80,15 @@ k_scan_single_block(int32_t *__restrict__ data, int64_t m) {
     const int32_t carry = s_carry;
     int32_t run = carry + (warp ? s_warp[warp - 1] : 0) + x - tot;     // exclusive prefix of this thread's first value
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { if (i0 + j < m) data[i0 + j] = run; run += v[j]; }
+    for (int j = 0; j < 32; ++j) { const int32_t t = v[j]; v[j] = run; run += t; }
+    if (vec && i0 + 32 <= m) {
+      int4 *p = reinterpret_cast<int4 *>(data + i0);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) p[q] = make_int4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (i0 + j < m) data[i0 + j] = v[j];
+    }
     __syncthreads();
     if (threadIdx.x == 1023) s_carry = carry + s_warp[31];
     __syncthreads();

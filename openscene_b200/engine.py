@@ -70,6 +70,37 @@ class FusedMinkUNet:
             raise RuntimeError("FusedMinkUNet folds BatchNorm running statistics: call model.eval() first")
         self.device = p.device
         self.dense_up = os.environ.get('OSB_DENSE_UP', '1') != '0'
+        # The packed weights and folded BatchNorm constants are COPIES: every tensor they were made from is tracked, and a
+        # forward that finds one changed (load_state_dict, an optimiser step, .to()) re-packs before it runs.
+        self._net = net
+        self._tracked = list(net.parameters()) + list(net.buffers())
+        self._build()
+        self.out_channels = self.final.cout
+        self.last_cm = None
+        self._ws = None
+        self._arena = None
+        self.use_pdl = os.environ.get('OSB_PDL', '1') != '0'
+        # persistent chain kernel (csrc/conv_chain.cu); OSB_CHAIN=0 restores one launch of the first-generation kernel per layer
+        self.use_chain = os.environ.get('OSB_CHAIN', '1') != '0'
+        self.chain_max_tiles = int(os.environ.get('OSB_CHAIN_MAX_TILES', '-1'))   # layers up to this many (row x N) tiles share a launch
+        self._chain = None
+        self.layer_log = None                     # profiling: set to [] to record (rows, K, cin, cout, tag) per convolution
+        self.use_pyramid = os.environ.get('OSB_PYRAMID', '1') != '0'
+        if 'OSB_TC_LAZY' in os.environ:                      # tuning: 0 = smem index prologue, 1 = lazy on >= 2-wave launches, 2 = always
+            tc.debug_set_tc(lazy=int(os.environ['OSB_TC_LAZY']))
+
+    def _signature(self):
+        return tuple((t._version, t.data_ptr()) for t in self._tracked)
+
+    def refresh(self):
+        """Re-pack the weights and re-fold BatchNorm from the source module (called automatically when a tracked tensor changed)."""
+        if self._net.training:
+            raise RuntimeError("FusedMinkUNet folds BatchNorm running statistics: call model.eval() first")
+        self._tracked = list(self._net.parameters()) + list(self._net.buffers())
+        self._build()
+
+    def _build(self):
+        net = self._net
         with torch.cuda.device(self.device), torch.no_grad():
             self.stem = _Conv(net.conv0p1s1, net.bn0, keep_f32=True)
             if self.stem.cin > 3 or self.stem.cout != 32:
@@ -91,19 +122,7 @@ class FusedMinkUNet:
                     up.n_ntiles = max(1, -(-(up.K * up.cout) // 256))
                 self.dec.append((up, self._blocks(getattr(net, f'block{j + 1}'))))
             self.final = _Conv(net.final, None, keep_f32=True)
-        self.out_channels = self.final.cout
-        self.last_cm = None
-        self._ws = None
-        self._arena = None
-        self.use_pdl = os.environ.get('OSB_PDL', '1') != '0'
-        # persistent chain kernel (csrc/conv_chain.cu); OSB_CHAIN=0 restores one launch of the first-generation kernel per layer
-        self.use_chain = os.environ.get('OSB_CHAIN', '1') != '0'
-        self.chain_max_tiles = int(os.environ.get('OSB_CHAIN_MAX_TILES', '-1'))   # layers up to this many (row x N) tiles share a launch
-        self._chain = None
-        self.layer_log = None                     # profiling: set to [] to record (rows, K, cin, cout, tag) per convolution
-        self.use_pyramid = os.environ.get('OSB_PYRAMID', '1') != '0'
-        if 'OSB_TC_LAZY' in os.environ:                      # tuning: 0 = smem index prologue, 1 = lazy on >= 2-wave launches, 2 = always
-            tc.debug_set_tc(lazy=int(os.environ['OSB_TC_LAZY']))
+        self._sig = self._signature()
 
     @staticmethod
     def _blocks(seq):
@@ -197,6 +216,8 @@ class FusedMinkUNet:
         """coords int32 [N,4] (batch,x,y,z), feats fp32 [N,cin], both CUDA, caller order.
         Returns fp32 [N, out_channels] in the caller's row order (== ``model(SparseTensor(feats, coords))``)."""
         C.require_cuda(feats, 'features')
+        if self._sig != self._signature():                     # the source module changed since the weights were packed
+            self.refresh()
         with torch.cuda.device(self.device):
             cm = coordinate_manager or CoordinateManager(coords, pyramid_levels=4 if self.use_pyramid else 0)
             self.last_cm = cm
@@ -319,14 +340,16 @@ class FusedMinkUNet:
         cv.scale = cv.shift = None
         cv.wpack_a, cv.wtiles_a, cv.scale_a, cv.shift_a = cv.wpack.data_ptr(), cv.wtiles.data_ptr(), 0, 0
         cv.n_ntiles = max(1, -(-cout // 256))
-        return (cv, cin, k)
+        return (cv, cin, k, self._signature())               # the signature lets forward_scores refuse a head folded from older weights
 
     @torch.no_grad()
     def forward_scores(self, coords, feats, folded, want_scores=True):
         """Cosine scores / labels of every voxel against the folded text set (``fold_head``), equal to
         ``match(normalize(forward(coords, feats)), text)`` up to rounding, without the 768-d features.
         Returns (scores fp16 [N,K] or None, label int64 [N], smax fp32 [N]) in the caller's row order."""
-        cv, cin, k = folded
+        cv, cin, k = folded[:3]
+        if len(folded) > 3 and folded[3] != self._signature():
+            raise RuntimeError("forward_scores: the folded head was built from weights that have changed since; call fold_head again")
         z = self.forward(coords, feats, head=cv)
         n = z.shape[0]
         scores = torch.empty((n, k), dtype=torch.float16, device=self.device) if want_scores else None

@@ -36,7 +36,7 @@ class OpenVocabSegmenter:
         np.fill_diagonal(self._matrix[:3, :3], 1.0 / voxel_size)
 
     def _fold(self):
-        if self._folded is None:
+        if self._folded is None or self._folded[3] != self.engine._signature():      # first use, or the model's weights changed
             self._folded = self.engine.fold_head(self.text.float())
         return self._folded
 

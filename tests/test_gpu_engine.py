@@ -45,6 +45,35 @@ def test_engine_refuses_train_mode():
         engine.FusedMinkUNet(model)
 
 
+def test_engine_follows_weight_changes():
+    """The engine's packed weights / folded BatchNorm are copies: in-place updates and load_state_dict must show up in the next
+    forward, and a head folded from the old weights must be refused (stale outputs with no error)."""
+    import MinkowskiEngine as ME
+    from openscene_b200 import engine
+    c = torch.from_numpy(synth.random_cloud(2500, 40, seed=6)).to(DEV)
+    f = torch.rand(c.shape[0], 3, device=DEV, generator=torch.Generator(device=DEV).manual_seed(3))
+    model = synth.build_model('MinkUNet14A', 64, seed=1).eval().to(DEV)
+    eng = engine.FusedMinkUNet(model)
+    text = torch.nn.functional.normalize(torch.randn(8, 64, device=DEV), dim=1)
+    head = eng.fold_head(text)
+    out0 = eng(c, f)
+    with torch.no_grad():
+        model.final.kernel.mul_(1.5)                                     # optimiser-style in-place update
+        model.bn0.bn.running_mean.add_(0.05)                             # a buffer, not a parameter
+        model.block2[0].conv1.kernel.add_(0.01)
+        ref = model(ME.SparseTensor(f, c))
+    out1 = eng(c, f)
+    assert rel_row_err(out1.cpu().numpy(), ref.cpu().numpy()) < 1e-3
+    assert rel_row_err(out1.cpu().numpy(), out0.cpu().numpy()) > 1e-2   # it really changed
+    with pytest.raises(RuntimeError, match='fold_head again'):
+        eng.forward_scores(c, f, head)
+    other = synth.build_model('MinkUNet14A', 64, seed=2).state_dict()
+    model.load_state_dict(other)
+    with torch.no_grad():
+        ref2 = model(ME.SparseTensor(f, c))
+    assert rel_row_err(eng(c, f).cpu().numpy(), ref2.cpu().numpy()) < 1e-3
+
+
 def test_folded_head_scores_match_materialised_path():
     """engine.forward_scores (final conv folded with the text matrix) against normalise + match on the 768-d features."""
     from openscene_b200 import engine, matching
