@@ -104,6 +104,30 @@ def test_conv_backward_matches_oracle_autograd():
         assert np.abs(ga - gb).max() / np.abs(ga).max() < 5e-5
 
 
+@pytest.mark.parametrize('cin,ks', [(3, 5), (1, 3), (4, 5), (2, 2)])
+def test_thin_stem_convolution_forward_and_wgrad_match_oracle(cin, ks):
+    """cin <= 4, cout == 32 (the 5x5x5 stem in training mode, models/mink_unet.py:47-49) runs on the lane-per-channel kernels of
+    csrc/conv_f32.cu: forward and weight gradient against oracle autograd in fp64."""
+    from openscene_b200 import me
+    from oracle import me_cpu
+    c = synth.random_cloud(3000, 30, seed=11, batch=2)
+    g = torch.Generator().manual_seed(4)
+    f = torch.randn(len(c), cin, generator=g)
+    torch.manual_seed(5)
+    co = me_cpu.MinkowskiConvolution(cin, 32, kernel_size=ks, dimension=3)
+    cg = me.MinkowskiConvolution(cin, 32, kernel_size=ks, dimension=3)
+    cg.load_state_dict(co.state_dict())
+    co.double(); cg.to(DEV)
+    yo = co(me_cpu.SparseTensor(f.double(), torch.from_numpy(c)))
+    yg = cg(me.SparseTensor(f.to(DEV), torch.from_numpy(c).to(DEV)))
+    assert rel_row_err(yg.F.detach().cpu().numpy(), yo.F.detach().numpy()) < 2e-5
+    w = torch.randn(len(c), 32, generator=g)
+    (yo.F * w.double()).sum().backward()
+    (yg.F * w.to(DEV)).sum().backward()
+    ga, gb = co.kernel.grad.numpy(), cg.kernel.grad.cpu().numpy()
+    assert ga.shape == gb.shape and np.abs(ga - gb).max() / np.abs(ga).max() < 5e-5
+
+
 def test_avg_pool_and_global_max():
     from openscene_b200 import me
     from oracle import me_cpu
