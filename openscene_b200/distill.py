@@ -44,16 +44,45 @@ def distill_loss(output_3d, feat_3d, loss_type='cosine'):
     raise NotImplementedError
 
 
-def distill_step(model, optimizer, coords, feats, feat_3d, mask, loss_type='cosine', translate=True):
+class _PassThrough(torch.nn.Module):
+    def forward(self, x):
+        return x
+
+
+def _late_head(model):
+    """(network, final) when the network ends in a bias-free 1x1x1 convolution applied row by row
+    (``self.final(out).F``, models/mink_unet.py:108-114,174), looked up through DDP (.module) and DisNet (.net3d)."""
+    m = model.module if hasattr(model, 'module') else model
+    m = m.net3d if hasattr(m, 'net3d') else m
+    fin = getattr(m, 'final', None)
+    if fin is not None and getattr(fin, 'use_mm', False) and getattr(fin, 'bias', None) is None and fin.kernel.dim() == 2:
+        return m, fin
+    return None, None
+
+
+def distill_step(model, optimizer, coords, feats, feat_3d, mask, loss_type='cosine', translate=True, late_head=True):
     """One training step, run/distill.py:311-334: random integer translation of the voxel grid (:315), forward
-    (BN in train mode), row select by ``mask`` (:322), cosine / L1 loss, backward (+ DDP all-reduce), Adam step."""
+    (BN in train mode), row select by ``mask`` (:322), cosine / L1 loss, backward (+ DDP all-reduce), Adam step.
+
+    late_head: the last layer is a 1x1x1 convolution, i.e. a per-row linear map, and the loss only sees the ``mask`` rows
+    (20 k of ~200 k voxels): ``final(x)[mask] == x[mask] @ W`` exactly, so the 96 -> 768 layer, its two gradients and the
+    [N, 768] select / scatter pair run on the supervised rows only.  Same loss, same gradients (up to fp32 summation order)."""
     import MinkowskiEngine as ME
     if translate:
         coords = coords.clone()
         coords[:, 1:4] += (torch.rand(3) * 100).type_as(coords)
     sinput = ME.SparseTensor(feats.cuda(non_blocking=True), coords.cuda(non_blocking=True))
-    output_3d = model(sinput)
-    output_3d = output_3d[mask.to(output_3d.device)]
+    net, fin = _late_head(model) if late_head else (None, None)
+    if net is not None:
+        net.final = _PassThrough()                    # the network returns the 96-d rows ...
+        try:
+            rows = model(sinput)
+        finally:
+            net.final = fin
+        output_3d = rows[mask.to(rows.device)] @ fin.kernel          # ... and the head runs on the supervised rows
+    else:
+        output_3d = model(sinput)
+        output_3d = output_3d[mask.to(output_3d.device)]
     loss = distill_loss(output_3d, feat_3d.to(output_3d.device), loss_type)
     optimizer.zero_grad()
     loss.backward()

@@ -86,3 +86,29 @@ def test_distill_step_reduces_loss():
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
     losses = [float(distill.distill_step(model, opt, c, f, tgt, mask)) for _ in range(6)]
     assert losses[-1] < losses[0] - 0.02, losses
+
+
+def test_distill_late_head_is_the_same_step():
+    """distill_step(late_head=True) applies the final 1x1x1 convolution to the supervised rows only: the loss and every
+    parameter gradient must equal the plain ``model(sinput)[mask]`` step (run/distill.py:321-333)."""
+    from openscene_b200 import distill
+    c = torch.from_numpy(synth.random_cloud(2000, 22, seed=12))
+    f = torch.ones(len(c), 3)
+    g = torch.Generator().manual_seed(8)
+    mask = torch.rand(len(c), generator=g) < 0.1
+    tgt = torch.randn(int(mask.sum()), 64, generator=g).half()
+
+    class Keep(torch.optim.SGD):                       # an optimiser that leaves the weights alone: gradients stay comparable
+        def step(self, closure=None):
+            return None
+    grads, losses = [], []
+    for late in (False, True):
+        model = synth.build_model('MinkUNet14A', 64, seed=1).to(DEV).train()
+        opt = Keep(model.parameters(), lr=0.0)
+        losses.append(float(distill.distill_step(model, opt, c, f, tgt, mask, translate=False, late_head=late)))
+        assert type(model.final).__name__ == 'MinkowskiConvolution'            # restored
+        grads.append({k: p.grad.clone() for k, p in model.named_parameters()})
+    assert abs(losses[0] - losses[1]) < 1e-5
+    for k in grads[0]:
+        a, b = grads[0][k], grads[1][k]
+        assert (a - b).abs().max() <= 2e-3 * a.abs().max() + 1e-8, k
