@@ -2,6 +2,7 @@
 
 "split rows": uint8 tensor [N, 4*C]; every 32-channel block is a 128-byte line [bf16 hi x32 | bf16 lo x32]."""
 import ctypes
+import weakref
 
 import torch
 
@@ -71,18 +72,25 @@ def conv_wgrad_tc(x_split, cin, n_in, nbr, n_out, K, gout_split, cout):
     return gw
 
 
-_PACK_CACHE = {}
+_PACK_CACHE = {}          # id(parameter) -> [weakref(parameter), version, address, {(transposed, shape): packed operand}]
 
 
 def packed_weights_cached(w3, transpose_w=False):
-    """``pack_weights`` memoised on (storage address, version counter): the packed operand is rebuilt only when the
-    parameter was written (optimizer step, load_state_dict), not on every forward / backward."""
-    key = (w3.data_ptr(), w3._version, bool(transpose_w), tuple(w3.shape))
-    hit = _PACK_CACHE.get(key)
+    """``pack_weights`` memoised per PARAMETER OBJECT and version counter: the packed operand is rebuilt only when the
+    parameter was written (optimizer step, load_state_dict), not on every forward / backward.  The entry holds a weak
+    reference to the parameter: an address + version key alone is not enough -- a freed model's storage is handed to the next
+    model with the same address and the same version 0, and a stale operand would be multiplied."""
+    base = w3._base if w3._base is not None else w3          # kernel.unsqueeze(0) of a 1x1x1 layer -> the parameter itself
+    ent = _PACK_CACHE.get(id(base))
+    if ent is None or ent[0]() is not base or ent[1] != base._version or ent[2] != base.data_ptr():
+        if len(_PACK_CACHE) > 2048:                             # drop the entries of parameters that no longer exist
+            for k in [k for k, e in _PACK_CACHE.items() if e[0]() is None]:
+                del _PACK_CACHE[k]
+        ent = _PACK_CACHE[id(base)] = [weakref.ref(base), base._version, base.data_ptr(), {}]
+    k = (bool(transpose_w), tuple(w3.shape))
+    hit = ent[3].get(k)
     if hit is None:
-        if len(_PACK_CACHE) > 1024:                     # stale versions of trained weights: drop everything, refill lazily
-            _PACK_CACHE.clear()
-        hit = _PACK_CACHE[key] = pack_weights(w3, transpose_w)
+        hit = ent[3][k] = pack_weights(w3, transpose_w)
     return hit
 
 
