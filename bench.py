@@ -406,16 +406,18 @@ def main():
         evs = []
         gc.collect()
         gc.disable()                                                 # no collector pauses between enqueues
-        for i in range(k):
-            flush.zero_()                                            # L2 flush, outside the timed events
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); fn(); b.record()
-            evs.append((a, b))
-            if sampler is not None and i in (k // 4, k // 2, (3 * k) // 4):
-                # on-device clock measurement, stream-ordered between two steps (outside their event pairs)
-                sampler.sample()
-        torch.cuda.synchronize()
-        gc.enable()
+        try:
+            for i in range(k):
+                flush.zero_()                                        # L2 flush, outside the timed events
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fn(); b.record()
+                evs.append((a, b))
+                if sampler is not None and i in (k // 4, k // 2, (3 * k) // 4):
+                    # on-device clock measurement, stream-ordered between two steps (outside their event pairs)
+                    sampler.sample()
+            torch.cuda.synchronize()
+        finally:
+            gc.enable()
         ts = sorted(a.elapsed_time(b) for a, b in evs)
         if tag:
             step_stats[tag] = {'min': ts[0], 'median': ts[len(ts) // 2], 'max': ts[-1]}
@@ -468,14 +470,22 @@ def main():
             else:
                 _, lab, _ = matching._scores(out, inv, text, normalize=True, want_scores=False)
             plabel_host.copy_(lab, non_blocking=True)
+        # extra measurement: never fail the headline.  Every rank passes the SAME two barriers whether or not its own
+        # attempt raised (a rank that skipped one would pair its next collective with the others' barrier).
+        ok_points = True
         try:
             for _ in range(2):
                 step_points()
-            barrier()
-            ms_points = timed(step_points, min(args.steps, 20)) / min(args.steps, 20)
-        except Exception as e:                                        # noqa: BLE001  (extra measurement: never fail the headline)
-            ms_points = None
+        except Exception as e:                                        # noqa: BLE001
+            ok_points = False
             print(f'[bench] e2e_points skipped: {e}', file=sys.stderr)
+        barrier()
+        if ok_points:
+            try:
+                ms_points = timed(step_points, min(args.steps, 20)) / min(args.steps, 20)
+            except Exception as e:                                    # noqa: BLE001
+                ms_points = None
+                print(f'[bench] e2e_points skipped: {e}', file=sys.stderr)
         barrier()
 
     # ---- optional re-associated head (not the headline: the 768-d features are not materialised) -----
