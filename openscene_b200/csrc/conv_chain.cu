@@ -785,6 +785,7 @@ int osb_conv_chain_grid(void) {
 }
 
 size_t osb_conv_chain_workspace_bytes(int64_t n_out, int32_t K, int32_t cin, int32_t cout) {
+  if (n_out <= 0 || K < 1 || cin < 32 || cout <= 0) return 0;     // shapes osb_conv_desc_fill rejects: nothing to reserve
   const int ns = chain_nsplit(n_out, K, cin, cout, osb_conv_chain_grid(), g_chain_force_split, g_chain_nsub);
   return ns > 1 ? (size_t)ns * n_out * chain_cout_pad(cout) * sizeof(float) : 0;
 }

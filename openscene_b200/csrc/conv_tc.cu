@@ -595,6 +595,7 @@ extern "C" {
 
 // bytes of caller-provided scratch osb_conv_fwd_tc may need for this shape (0 = none)
 size_t osb_conv_tc_workspace_bytes(int64_t n_out, int32_t K, int32_t cin, int32_t cout) {
+  if (n_out <= 0 || K < 1 || cin < 32 || cout <= 0) return 0;     // shapes osb_conv_fwd_tc rejects: nothing to reserve
   const int cp = cout_pad_of(cout);
   const int nt = choose_nt(n_out, cp);
   const int64_t ctas = ceil_div(n_out, TC_M) * (cp / nt);

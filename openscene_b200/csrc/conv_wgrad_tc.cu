@@ -217,6 +217,7 @@ static void wgrad_plan(int64_t n_out, int K, int cin, int cout, int *n_mt, int *
 extern "C" {
 
 size_t osb_conv_wgrad_tc_workspace_bytes(int64_t n_out, int32_t K, int32_t cin, int32_t cout) {
+  if (n_out <= 0 || K < 1 || cin < 32 || cout < 32) return 0;     // shapes osb_conv_wgrad_tc rejects: nothing to reserve
   int n_mt, n_nt, n_rs; int64_t rpr;
   wgrad_plan(n_out, K, cin, cout, &n_mt, &n_nt, &n_rs, &rpr);
   return (size_t)K * n_mt * n_nt * n_rs * 128 * 256 * sizeof(float);
