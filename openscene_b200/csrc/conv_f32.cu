@@ -328,6 +328,7 @@ int osb_conv_wgrad_f32(const float *in, const int32_t *nbr, int64_t n_out, int32
 int osb_gather_rows_f32(const float *in, const int32_t *idx, int64_t n_out, int32_t c, float *out, void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (n_out == 0) return 0;
+  OSB_CHECK(n_out > 0 && c > 0 && in && idx && out, "osb_gather_rows_f32: bad arguments (n_out %lld, c %d)", (long long)n_out, c);
   const int64_t total = n_out * c;
   unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(total, 256), 148 * 16);
   k_gather_rows_f32<<<blocks, 256, 0, stream>>>(in, idx, n_out, c, out);

@@ -83,6 +83,7 @@ __global__ void k_measure_sm_mhz(float *__restrict__ out) {
 }  // namespace osb
 
 extern "C" int osb_measure_sm_mhz(float *mhz_dev, void *stream_) {
+  OSB_CHECK(mhz_dev != nullptr, "osb_measure_sm_mhz: null output");
   osb::k_measure_sm_mhz<<<1, 1, 0, (cudaStream_t)stream_>>>(mhz_dev);
   OSB_LAUNCH_CHECK();
   return 0;
