@@ -10,7 +10,8 @@ A step = one synthetic ScanNet-shaped scene (BASELINE.json configs[1]: ~200k vox
 `value`  : voxels/s with coords/feats already in HBM (whole job, all ranks).
 `e2e`    : same metric through the public API with pinned HOST buffers: H2D of coords/feats and D2H of the labels
            inside the timed region.
-Scenes shard one per GPU with no data-path collective (weak scaling); timing = CUDA events, max over ranks.
+One scene per GPU with no data-path collective; every rank processes the same seed-0 scene, i.e. the work per GPU is
+fixed as N grows (weak scaling; see scene_seed); timing = CUDA events, max over ranks.
 """
 import argparse
 import json
@@ -157,12 +158,23 @@ def host_threads():
     return max(1, min(n, int(os.environ.get('OSB_CPU_THREADS', 16))))
 
 
+def scene_seed(rank):
+    """Weak scaling = the work per GPU is fixed as N grows, so every rank processes the SAME scene (seed 0, the N=1 workload).
+    With per-rank seeds the generator's scenes differ by up to +-8 % in voxel count (seeds 0..7 of config2_200k: 197382, 202435,
+    188286, 180984, 195133, 211036, 200222, 207840) and every rank repeats its own scene for all K steps: the max-over-ranks
+    time is then the largest scene's while `value` counts the mean -- a persistent imbalance a real run over many scenes per
+    rank does not have (no per-step synchronisation in inference).  OSB_BENCH_SCENES=distinct restores one seed per rank."""
+    return rank if os.environ.get('OSB_BENCH_SCENES', 'same') == 'distinct' else 0
+
+
 def workload_config(args, n_vox):
     """The `config` object, identical in both arms (the driver compares them)."""
     return {'workload': f'{args.workload}: {n_vox} voxels/scene, one scene per GPU, {args.arch}, 768-d head, '
                         f'K_text={args.k_text}, ' + ('ensemble matching (2 cosine products + select + final product, run/evaluate.py:302-323)'
                                                       if getattr(args, 'match', 'cosine') == 'ensemble' else 'cosine (L2-normalised) scores') + ' + argmax',
             'points': 'stride-1 voxels fed to SparseTensor',
+            'scenes': ('one generator seed per rank (OSB_BENCH_SCENES=distinct)' if os.environ.get('OSB_BENCH_SCENES', 'same') == 'distinct'
+                       else 'every rank processes the same seed-0 scene: per-GPU work exactly fixed (weak scaling)'),
             'l2': 'GPU arm: L2 flushed (256 MiB memset) before every timed step; CPU arm: working set (~2 GB of activations) '
                   'far beyond the last-level cache'}
 
@@ -218,7 +230,7 @@ def run_distill(args, rank, local, world):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     arch = args.arch if args.arch != 'MinkUNet34C' or os.environ.get('OSB_DISTILL_34C') else 'MinkUNet18A'
-    coords_np = synth.scene('config2_200k', seed=rank)
+    coords_np = synth.scene('config2_200k', seed=scene_seed(rank))
     n0 = len(coords_np)
     g = torch.Generator().manual_seed(100 + rank)
     m_sup = min(20_000, n0)
@@ -306,6 +318,8 @@ def run_distill(args, rank, local, world):
                 'config': {'workload': f'config3_distill: one config2_200k scene ({n0} voxels) per GPU, {arch}, 768-d head, '
                                        f'{m_sup} supervised voxels, cosine loss, Adam, DDP/NCCL gradient all-reduce of '
                                        f'{n_par * 4 / 1e6:.0f} MB', 'points': 'stride-1 voxels fed to SparseTensor',
+                           'scenes': ('one generator seed per rank' if scene_seed(1) else 'every rank trains on the same seed-0 scene '
+                                      '(per-GPU work exactly fixed); supervision mask and target features differ per rank'),
                            'l2': 'flushed (256 MiB memset) before every timed step'},
                 'e2e': {'value': value, 'unit': 'voxels/s', 'ms_per_step': t_all / args.steps,
                         'h2d_bytes_per_step': int(coords_h.numel() * 4 + feats_h.numel() * 4 + feat3d_h.numel() * 2 + mask_h.numel()),
@@ -353,7 +367,7 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
 
     # ---- workload: one scene per rank (weak scaling), seeded by rank ---------------------------------
-    coords_np = synth.scene(args.workload, seed=rank)
+    coords_np = synth.scene(args.workload, seed=scene_seed(rank))
     n0 = len(coords_np)
     coords_host = torch.from_numpy(coords_np).pin_memory()
     feats_host = torch.ones(n0, 3).pin_memory()                      # dataset/feature_loader.py:184
@@ -453,7 +467,7 @@ def main():
     ms_points, n_pts = None, 0
     if not args.modules:
         from openscene_b200.voxelize import voxelize_points
-        pts_np, vsize = synth.scene_points(args.workload, seed=rank)
+        pts_np, vsize = synth.scene_points(args.workload, seed=scene_seed(rank))
         n_pts = len(pts_np)
         pts_host = torch.from_numpy(pts_np.astype(np.float32)).pin_memory()
         Mv = np.eye(4); Mv[0, 0] = Mv[1, 1] = Mv[2, 2] = 1.0 / vsize
