@@ -89,3 +89,41 @@ def test_reference_model_file_forwards_on_the_gpu(arch):
     with torch.no_grad():
         out = model(ME.SparseTensor(torch.from_numpy(g['feats']).cuda(), torch.from_numpy(g['coords']).cuda()))
     assert rel_row_err(out.cpu().numpy()[g['rows']], g['out_rows']) < 1e-3
+
+
+ALL_ARCHS = ['MinkUNet14A', 'MinkUNet14B', 'MinkUNet14C', 'MinkUNet14D', 'MinkUNet18A', 'MinkUNet18B', 'MinkUNet18D',
+             'MinkUNet34A', 'MinkUNet34B', 'MinkUNet34C']
+
+
+@needs_ref
+@pytest.mark.parametrize('arch', [a for a in ALL_ARCHS if a not in ('MinkUNet18A', 'MinkUNet34C')])
+def test_every_factory_architecture_matches_the_mirror(arch):
+    """The eight other names `mink_unet()` accepts (models/mink_unet.py:241-263): the reference's class on the product package and
+    the table-driven mirror give the same state-dict keys, shapes and seeded weights, and load each other's checkpoints."""
+    mu, _ = _import_reference_models()
+    from openscene_b200 import minkunet
+    torch.manual_seed(0)
+    ref = mu.mink_unet(in_channels=3, out_channels=20, D=3, arch=arch)
+    torch.manual_seed(0)
+    mir = minkunet.mink_unet(in_channels=3, out_channels=20, D=3, arch=arch)
+    sd, msd = ref.state_dict(), mir.state_dict()
+    assert list(sd.keys()) == list(msd.keys())
+    for k in sd:
+        assert sd[k].shape == msd[k].shape and torch.equal(sd[k], msd[k]), k
+    mir.load_state_dict(sd, strict=True)
+    ref.load_state_dict(msd, strict=True)
+
+
+@needs_ref
+def test_factory_rejects_what_the_reference_rejects():
+    """`mink_unet(arch=...)` raises for names outside its list -- MinkUNet50 / MinkUNet101 included: the reference defines those
+    classes (models/mink_unet.py:191-199) but gives them no PLANES, so they cannot be constructed there either."""
+    mu, _ = _import_reference_models()
+    from openscene_b200 import minkunet
+    for arch in ('MinkUNet50', 'MinkUNet101', 'nonsense'):
+        with pytest.raises(Exception):
+            mu.mink_unet(arch=arch)
+        with pytest.raises(Exception):
+            minkunet.mink_unet(arch=arch)
+    with pytest.raises(TypeError):                      # PLANES is None: self.PLANES[0] fails in network_initialization
+        mu.MinkUNet50(3, 20, 3)
