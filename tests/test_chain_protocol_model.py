@@ -288,8 +288,9 @@ def _items(rng, n, max_stages):
     return items, ends[:-1]
 
 
-# the ring shapes osb_conv_chain_launch builds: even row rings of 4..12 slots, 2 or 3 weight slots (up to CH_MAX_SB = 4)
-RINGS = [(4, 2), (6, 3), (8, 2), (10, 3), (12, 3), (12, 2), (10, 4)]
+# the ring shapes osb_conv_chain_launch builds: even row rings of 4..12 slots, 2 or 3 weight slots (up to CH_MAX_SB = 4);
+# the defaults are (10, 3) for N tiles up to 96 columns, (8, 3) for 128 and (8, 2) for 256
+RINGS = [(4, 2), (6, 3), (8, 2), (8, 3), (10, 3), (12, 3), (12, 2), (10, 4)]
 
 
 @pytest.mark.parametrize('sa,sb', RINGS)
