@@ -424,10 +424,10 @@ class MinkowskiConvolutionTranspose(_ConvBase):
 
 
 class MinkowskiBatchNorm(nn.Module):
-    _osb_me_op = True      # an operator of this package (fast_eval.py looks for the module that CALLS them)
     """Same structure as the reference stack: an ``nn.BatchNorm1d`` under ``.bn`` applied to the
     [N,C] feature matrix (resnet_base.py:79-80 touches ``m.bn.weight``).  The fused inference
     engine folds it into the convolution epilogue instead (openscene_b200/engine.py)."""
+    _osb_me_op = True      # an operator of this package (fast_eval.py looks for the module that CALLS them)
 
     def __init__(self, num_features, eps=1e-5, momentum=0.1, affine=True, track_running_stats=True):
         super().__init__()
