@@ -241,3 +241,28 @@ def test_checker_catches_a_missing_barrier(recorded, monkeypatch):
     monkeypatch.setattr(engine.FusedMinkUNet, '_conv', conv)
     with pytest.raises(AssertionError, match='without a barrier'):
         test_launch_plan_has_no_unordered_dependency(recorded, 'MinkUNet34C', 'bench')
+
+
+def test_folded_head_is_the_same_cosine_score(recorded):
+    """``fold_head`` re-associates the last layer with the text matrix (W W^T = L L^T, U = W T^T) so that the [N,768] features
+    are never written.  The algebra, on the CPU in fp64: for rows x, (x U_k) / |x L| equals cos(x W, T_k), and the packed
+    96 -> 96 + K convolution the engine launches carries exactly [L | U]."""
+    model = synth.build_model('MinkUNet34C', 768, seed=0).eval()
+    eng = engine.FusedMinkUNet(model)
+    text = torch.from_numpy(synth.text_embeddings(20)).float()
+    cv, cin, k, sig = eng.fold_head(text)
+    assert (cin, k) == (96, 20) and cv.cout % 32 == 0 and cv.cout >= cin + k and sig == eng._signature()
+    W = model.final.kernel.detach().double()                         # [96, 768]
+    x = torch.randn(500, 96, dtype=torch.float64)
+    z = x @ cv.w3[0].double()                                        # what the folded convolution produces per row
+    got = z[:, cin:cin + k] / z[:, :cin].norm(dim=1, keepdim=True)
+    f = x @ W
+    want = (f / f.norm(dim=1, keepdim=True)) @ text.double().t()     # run/evaluate.py:305-310: text rows used as they are
+    assert float((got - want).abs().max()) < 1e-6                    # fp32 storage of L and U (scores are rounded to fp16 later)
+    assert torch.all(cv.w3[0, :, cin + k:] == 0)                     # padding columns
+    # a head folded from older weights is refused (the engine re-packs, the signature moves on)
+    with torch.no_grad():
+        model.final.kernel.mul_(1.5)
+    n = SCENES['tiny']
+    with pytest.raises(RuntimeError, match='folded head was built from weights that have changed'):
+        eng.forward_scores(torch.zeros(n[0], 4, dtype=torch.int32), torch.ones(n[0], 3), (cv, cin, k, sig))
